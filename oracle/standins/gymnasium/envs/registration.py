@@ -1,0 +1,5 @@
+REGISTRY = {}
+
+
+def register(id, entry_point=None, **kwargs):
+    REGISTRY[id] = entry_point
