@@ -1,0 +1,134 @@
+"""ctypes binding of libquadsim.so (C ABI: include/quadsim.h).
+
+The CUDA library is the product: if it is missing or does not load this module
+raises -- there is no CPU or PyTorch fallback anywhere in the package.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libquadsim.so")
+SOURCES = [os.path.join(_HERE, "csrc", "quadsim.cu")]
+HEADERS = [os.path.join(_HERE, "csrc", "quad_core.cuh"), os.path.join(_ROOT, "include", "quadsim.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# enums of include/quadsim.h
+MODEL_CF2X, MODEL_CF2P, MODEL_RACE = 0, 1, 2
+ACT_RPM, ACT_PID, ACT_VEL, ACT_ONE_D_RPM, ACT_ONE_D_PID, ACT_RAW_RPM = 0, 1, 2, 3, 4, 5
+TASK_NONE, TASK_HOVER = 0, 1
+EFFECT_GND, EFFECT_DRAG, EFFECT_DW = 1, 2, 4
+FLAG_AUTORESET_SAME_STEP, FLAG_AUTORESET_NEXT_STEP, FLAG_RPY_F32 = 1, 2, 4
+FLAG_AUTORESET_CLEARS_PID, FLAG_AUTORESET_CLEARS_HISTORY = 8, 16
+FLAG_SKIP_EPILOGUE, FLAG_RPM_FROM_LAST = 0x100, 0x200
+ABI_VERSION = 1
+
+_d = C.c_double
+
+
+class QsParams(C.Structure):
+    _fields_ = [
+        ("dt", _d), ("ctrl_dt", _d), ("pyb_freq", _d), ("m", _d), ("gravity", _d), ("kf", _d), ("km", _d),
+        ("j", _d * 3), ("j_inv", _d * 3), ("hover_rpm", _d), ("max_rpm", _d),
+        ("sx", _d * 4), ("sy", _d * 4), ("sz", _d * 4), ("kx", _d), ("ky", _d),
+        ("gnd_eff_coeff", _d), ("prop_radius", _d), ("gnd_eff_h_clip", _d), ("prop_xyz", (_d * 3) * 4),
+        ("drag_coeff", _d * 3), ("dw_coeff", _d * 3),
+        ("episode_len_sec", _d), ("xy_bound", _d), ("z_bound", _d), ("tilt_bound", _d), ("term_dist", _d),
+        ("speed_limit", _d),
+        ("pid_p_for", _d * 3), ("pid_i_for", _d * 3), ("pid_d_for", _d * 3),
+        ("pid_p_tor", _d * 3), ("pid_i_tor", _d * 3), ("pid_d_tor", _d * 3),
+        ("pid_mixer", (_d * 3) * 4),
+        ("pid_pwm2rpm_scale", _d), ("pid_pwm2rpm_const", _d), ("pid_min_pwm", _d), ("pid_max_pwm", _d),
+        ("pid_gravity", _d), ("pid_kf", _d),
+        ("drone_model", C.c_int), ("pad_", C.c_int),
+    ]
+
+
+class QsState(C.Structure):
+    _fields_ = [
+        ("planes", C.c_void_p), ("last_rpm", C.c_void_p), ("step_counter", C.c_void_p), ("pending_reset", C.c_void_p),
+        ("pid", C.c_void_p), ("init_pos", C.c_void_p), ("init_quat", C.c_void_p), ("target_pos", C.c_void_p),
+        ("tables_per_env", C.c_int), ("pad_", C.c_int),
+    ]
+
+
+class QsStepIO(C.Structure):
+    _fields_ = [
+        ("action", C.c_void_p), ("obs_prev", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
+        ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("final_obs", C.c_void_p), ("dw_fz", C.c_void_p),
+        ("act_buffer_size", C.c_int), ("tick_substeps", C.c_int),
+    ]
+
+
+EXPORTS = ["qs_abi_version", "qs_last_error", "qs_sizeof_params", "qs_sizeof_state", "qs_sizeof_step_io",
+           "qs_step", "qs_dyn_substeps", "qs_pid_control", "qs_downwash", "qs_reset"]
+
+
+def build(force=False, verbose=False):
+    """Compile libquadsim.so in-tree for sm_100a with nvcc (no torch headers; a few seconds)."""
+    newest_src = max(os.path.getmtime(p) for p in SOURCES + HEADERS)
+    if not force and os.path.isfile(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest_src:
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libquadsim.so")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Loads (once) and returns the CUDA library.  Raises if it is not built: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError("libquadsim.so is not built (%s).  Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or gym_pybullet_drones_b200._native.build().  There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.qs_abi_version.restype = C.c_int
+    L.qs_last_error.restype = C.c_char_p
+    for n in ("qs_sizeof_params", "qs_sizeof_state", "qs_sizeof_step_io"):
+        getattr(L, n).restype = C.c_int
+    L.qs_step.restype = C.c_int
+    L.qs_step.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.POINTER(QsStepIO), C.c_int, C.c_int,
+                          C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
+    L.qs_dyn_substeps.restype = C.c_int
+    L.qs_dyn_substeps.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
+    L.qs_pid_control.restype = C.c_int
+    L.qs_pid_control.argtypes = [C.POINTER(QsParams), C.c_void_p, C.c_double,
+                                 C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.qs_downwash.restype = C.c_int
+    L.qs_downwash.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.qs_reset.restype = C.c_int
+    L.qs_reset.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.c_void_p, C.c_int, C.c_int,
+                           C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    if L.qs_abi_version() != ABI_VERSION:
+        raise ImportError("libquadsim.so ABI %d != binding ABI %d: rebuild" % (L.qs_abi_version(), ABI_VERSION))
+    if (L.qs_sizeof_params(), L.qs_sizeof_state(), L.qs_sizeof_step_io()) != (C.sizeof(QsParams), C.sizeof(QsState), C.sizeof(QsStepIO)):
+        raise ImportError("libquadsim.so struct layout differs from the ctypes mirror: rebuild")
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    """Maps the C-ABI error convention to exceptions (the reference prints '[ERROR]' and exit()s)."""
+    if rc == 0:
+        return
+    msg = lib().qs_last_error().decode()
+    if rc < 0:
+        raise ValueError("%s: %s (QS_ERR %d)" % (what, msg, rc))
+    raise RuntimeError("%s: CUDA error %d: %s" % (what, rc, msg))

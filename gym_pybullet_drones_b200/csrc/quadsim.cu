@@ -1,0 +1,612 @@
+// quadsim.cu -- sm_100a kernels + C ABI (include/quadsim.h) of the vectorised quadrotor simulator.
+//
+// One thread per drone advances the whole control tick in float64 registers (action decode -> S substeps of
+// explicit dynamics -> derived rpy/ang_v -> task terms); the CTA then writes its contiguous span of observation
+// rows cooperatively so every global access is coalesced:
+//   state   : 4 float4 planes [4][N] (16-byte ld/st.global.v4 per thread, fully coalesced)
+//   obs     : row-major [N][12+B*A]; a CTA owns rows [c0, c0+T) = one contiguous span; the kinematic head of each
+//             row is staged in shared memory by the owning thread, the action history is streamed
+//             prev_obs -> obs by whole warps (lane = column), shifted by one action
+//   consts  : QsParams travels in the kernel parameter (constant bank, uniform operand -- no load instruction)
+// No tensor cores: the path is element-wise; the roofline that bounds it is HBM bandwidth.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "quad_core.cuh"
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+int fail(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kMaxTPB = 128;          // threads (= drones) per CTA upper bound
+
+struct StepArgs {
+    QsParams P;
+    QsState st;
+    QsStepIO io;
+    int act_type, task, n_envs, D, substeps, N, A, obs_dim, tpb, counter_inc;
+    unsigned effects, flags;
+};
+
+__device__ __forceinline__ float4 ldg4(const float* base, long long idx4) {
+    return __ldg(reinterpret_cast<const float4*>(base) + idx4);
+}
+__device__ __forceinline__ void st4(float* base, long long idx4, float4 v) {
+    reinterpret_cast<float4*>(base)[idx4] = v;
+}
+
+// split a double into float32 hi + float32 lo (hi + lo carries ~48 bits)
+__device__ __forceinline__ void split2(double v, float& hi, float& lo) {
+    hi = (float)v;
+    lo = (float)(v - (double)hi);
+}
+
+__device__ __forceinline__ void load_drone(const float* planes, long long N, long long i, qs::Drone& d) {
+    const float4 p0 = ldg4(planes, i), p1 = ldg4(planes, N + i), p2 = ldg4(planes, 2 * N + i), p3 = ldg4(planes, 3 * N + i);
+    d.px = p0.x; d.py = p0.y; d.pz = p0.z;
+    d.qx = p1.x; d.qy = p1.y; d.qz = p1.z; d.qw = p1.w;
+    d.vx = p2.x; d.vy = p2.y; d.vz = p2.z;
+    d.wx = (double)p0.w + (double)p3.y;
+    d.wy = (double)p2.w + (double)p3.z;
+    d.wz = (double)p3.x + (double)p3.w;
+}
+
+// normalises the quaternion (the north-star's "quaternion renormalise"; Bullet's own read-back goes through a
+// rotation matrix and renormalises too) and stores the 4 planes
+__device__ __forceinline__ void store_drone(float* planes, long long N, long long i, qs::Drone& d) {
+    const double inv = rsqrt(d.qx * d.qx + d.qy * d.qy + d.qz * d.qz + d.qw * d.qw);
+    d.qx *= inv; d.qy *= inv; d.qz *= inv; d.qw *= inv;
+    float wxh, wxl, wyh, wyl, wzh, wzl;
+    split2(d.wx, wxh, wxl); split2(d.wy, wyh, wyl); split2(d.wz, wzh, wzl);
+    st4(planes, i, make_float4((float)d.px, (float)d.py, (float)d.pz, wxh));
+    st4(planes, N + i, make_float4((float)d.qx, (float)d.qy, (float)d.qz, (float)d.qw));
+    st4(planes, 2 * N + i, make_float4((float)d.vx, (float)d.vy, (float)d.vz, wyh));
+    st4(planes, 3 * N + i, make_float4(wzh, wxl, wyl, wzl));
+}
+
+__device__ __forceinline__ void init_drone(const QsState& st, long long tbl, qs::Drone& d) {
+    const float4 ip = ldg4(st.init_pos, tbl), iq = ldg4(st.init_quat, tbl);
+    d.px = ip.x; d.py = ip.y; d.pz = ip.z;
+    d.qx = iq.x; d.qy = iq.y; d.qz = iq.z; d.qw = iq.w;
+    d.vx = d.vy = d.vz = 0.0;
+    d.wx = d.wy = d.wz = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused control tick.  RAW = CtrlAviary semantics (clip raw rpm, [N][20] state vectors out, no task).
+// Block = tpb threads, tpb a multiple of D (drones of one aviary never straddle CTAs) when D <= 128.
+// ---------------------------------------------------------------------------------------------------------
+template <int EFF, bool RAW>
+__global__ void __launch_bounds__(kMaxTPB) step_kernel(const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const QsParams& P = a.P;
+    const int tpb = a.tpb, D = a.D, A = a.A;
+    const int t = threadIdx.x;
+    const long long N = a.N;
+    const long long c0 = (long long)blockIdx.x * tpb;          // first drone of this CTA
+    const long long i = c0 + t;
+    const bool live = (t < tpb) && (i < N);
+    const int head = RAW ? 20 : 12;                            // floats staged per row
+    // shared layout
+    float* head_s = reinterpret_cast<float*>(smem_raw);                  // [tpb][head]
+    float* act_s = head_s + (size_t)kMaxTPB * 20;                        // [tpb][4]
+    double* red_s = reinterpret_cast<double*>(act_s + (size_t)kMaxTPB * 4);   // [tpb][2] reward, dist
+    double* pos_s = red_s + (size_t)kMaxTPB * 2;                         // [tpb][3] (in-CTA downwash)
+    unsigned char* oob_s = reinterpret_cast<unsigned char*>(pos_s + (size_t)kMaxTPB * 3);   // [tpb]
+    unsigned char* mode_s = oob_s + kMaxTPB;                             // [tpb] row mode: 0 shift, 1 keep history, 2 also final_obs
+    unsigned char* done_s = mode_s + kMaxTPB;                            // [tpb] per local env
+
+    const long long e = live ? i / D : 0;
+    const int le = t / D;                                      // local env (meaningful when D <= tpb)
+    const int dslot = (int)(i - e * D);                        // drone index inside its aviary
+    const long long tbl = a.st.tables_per_env ? i : dslot;
+
+    qs::Drone d;
+    qs::Derived o;
+    qs::PidState pst = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float act[4] = {0.f, 0.f, 0.f, 0.f};
+    double rpm[4] = {0, 0, 0, 0}, rpm_prev[4] = {0, 0, 0, 0};
+    double R_last[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    int sc = 0;
+    bool pending = false;
+    const bool pid_act = (a.act_type == QS_ACT_PID || a.act_type == QS_ACT_VEL || a.act_type == QS_ACT_ONE_D_PID);
+
+    if (live) {
+        load_drone(a.st.planes, N, i, d);
+        if (A == 4) {
+            const float4 v = ldg4(a.io.action, i);
+            act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
+        } else {
+            for (int k = 0; k < A; ++k) act[k] = __ldg(a.io.action + i * A + k);
+        }
+        if (((EFF & QS_EFFECT_DRAG) || (a.flags & QS_FLAG_RPM_FROM_LAST)) && a.st.last_rpm) {
+            const float4 v = ldg4(a.st.last_rpm, i);
+            rpm_prev[0] = v.x; rpm_prev[1] = v.y; rpm_prev[2] = v.z; rpm_prev[3] = v.w;
+        }
+        if (pid_act) {
+            const float* ps = a.st.pid;
+            pst.ipx = ps[i]; pst.ipy = ps[N + i]; pst.ipz = ps[2 * N + i];
+            pst.lr = ps[3 * N + i]; pst.lp = ps[4 * N + i]; pst.ly = ps[5 * N + i];
+            pst.irx = ps[6 * N + i]; pst.iry = ps[7 * N + i]; pst.irz = ps[8 * N + i];
+        }
+        sc = a.st.step_counter[e];
+        if ((a.flags & QS_FLAG_AUTORESET_NEXT_STEP) && a.st.pending_reset) pending = a.st.pending_reset[e] != 0;
+    }
+
+    if (live && !pending) {
+        double cur_yaw = 0.0;
+        if (a.act_type == QS_ACT_VEL) {
+            double r_, p_;
+            qs::quat_to_euler<false>(d.qx, d.qy, d.qz, d.qw, r_, p_, cur_yaw);
+        }
+        if (a.flags & QS_FLAG_RPM_FROM_LAST) {
+            rpm[0] = rpm_prev[0]; rpm[1] = rpm_prev[1]; rpm[2] = rpm_prev[2]; rpm[3] = rpm_prev[3];
+        } else {
+            qs::decode_action(P, RAW ? (int)QS_ACT_RAW_RPM : a.act_type, act, d, cur_yaw, pst, rpm);
+        }
+    }
+
+    // ---- physics: S substeps ------------------------------------------------------------------------------
+    if ((EFF & QS_EFFECT_DW) && a.io.dw_fz == nullptr) {
+        // downwash inside the CTA: all drones of an aviary sit in this CTA (D <= tpb), positions go through smem
+        for (int s = 0; s < a.substeps; ++s) {
+            if (live) { pos_s[3 * t] = d.px; pos_s[3 * t + 1] = d.py; pos_s[3 * t + 2] = d.pz; }
+            __syncthreads();
+            double fz = 0.0;
+            if (live && !pending) {
+                const int b = le * D;
+                for (int k = 0; k < D; ++k) {                                   // BaseAviary.py:798-811
+                    const double dz = pos_s[3 * (b + k) + 2] - d.pz;
+                    const double dx = pos_s[3 * (b + k)] - d.px, dy = pos_s[3 * (b + k) + 1] - d.py;
+                    const double dxy2 = dx * dx + dy * dy;
+                    if (dz > 0.0 && dxy2 < 100.0) fz += qs::downwash_pair(P, dz, dxy2);
+                }
+                qs::dyn_tick<EFF>(P, d, rpm, s == 0 ? rpm_prev : rpm, fz, 1, R_last);
+            }
+            __syncthreads();
+        }
+    } else if (live && !pending) {
+        const double fz = (EFF & QS_EFFECT_DW) ? (double)__ldg(a.io.dw_fz + i) : 0.0;
+        qs::dyn_tick<EFF>(P, d, rpm, rpm_prev, fz, a.substeps, R_last);
+    }
+
+    // ---- derived outputs, task terms --------------------------------------------------------------------
+    bool env_done = false;
+    if (live) {
+        if (pending) {                       // NEXT_STEP autoreset: this call only resets the env
+            init_drone(a.st, tbl, d);
+            if (a.flags & QS_FLAG_AUTORESET_CLEARS_PID) pst = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        }
+        if (a.flags & QS_FLAG_RPY_F32) qs::derive<true>(d, R_last, o); else qs::derive<false>(d, R_last, o);
+        if (pending) { o.ax = o.ay = o.az = 0.0; }
+    }
+    const bool want_epilogue = !(a.flags & QS_FLAG_SKIP_EPILOGUE);
+    if (!RAW && a.task == QS_TASK_HOVER && want_epilogue) {
+        if (live) {
+            const float4 tp = ldg4(a.st.target_pos, tbl);
+            const qs::TaskTerms tt = qs::hover_terms(P, d, o, tp.x, tp.y, tp.z);
+            red_s[2 * t] = tt.reward; red_s[2 * t + 1] = tt.dist; oob_s[t] = tt.out_of_bounds ? 1 : 0;
+        }
+        __syncthreads();
+        if (live && dslot == 0) {
+            double rew = 0.0, dist = 0.0; bool oob = false;
+            for (int k = 0; k < D; ++k) { rew += red_s[2 * (t + k)]; dist += red_s[2 * (t + k) + 1]; oob |= oob_s[t + k] != 0; }
+            bool term = dist < P.term_dist;                                        // HoverAviary.py:91
+            bool trunc = oob || ((double)sc / P.pyb_freq > P.episode_len_sec);     // HoverAviary.py:113
+            if (pending) { rew = 0.0; term = false; trunc = false; }
+            a.io.reward[e] = (float)rew;
+            a.io.terminated[e] = term ? 1 : 0;
+            a.io.truncated[e] = trunc ? 1 : 0;
+            done_s[le] = (term || trunc) ? 1 : 0;
+        }
+        __syncthreads();
+        if (live) env_done = done_s[le] != 0;
+    } else if (!RAW && want_epilogue && live && dslot == 0) {
+        a.io.reward[e] = -1.0f; a.io.terminated[e] = 0; a.io.truncated[e] = 0;     // CtrlAviary-style dummy task
+    }
+
+    // ---- stage this drone's row head, autoreset, store state ---------------------------------------------
+    if (live) {
+        float* h = head_s + (size_t)t * head;
+        // row mode bits: 1 = keep history unshifted, 2 = also copy the row to final_obs, 4 = zero the history in obs
+        unsigned char mode = pending ? (unsigned char)(1 | ((a.flags & QS_FLAG_AUTORESET_CLEARS_HISTORY) ? 4 : 0)) : (unsigned char)0;
+        if (RAW) {
+            // _getDroneStateVector (BaseAviary.py:541-561); quaternion reported normalised
+            const double inv = rsqrt(d.qx * d.qx + d.qy * d.qy + d.qz * d.qz + d.qw * d.qw);
+            h[0] = (float)d.px; h[1] = (float)d.py; h[2] = (float)d.pz;
+            h[3] = (float)(d.qx * inv); h[4] = (float)(d.qy * inv); h[5] = (float)(d.qz * inv); h[6] = (float)(d.qw * inv);
+            h[7] = (float)o.roll; h[8] = (float)o.pitch; h[9] = (float)o.yaw;
+            h[10] = (float)d.vx; h[11] = (float)d.vy; h[12] = (float)d.vz;
+            h[13] = (float)o.ax; h[14] = (float)o.ay; h[15] = (float)o.az;
+            h[16] = (float)rpm[0]; h[17] = (float)rpm[1]; h[18] = (float)rpm[2]; h[19] = (float)rpm[3];
+        } else {
+            const bool same_step = (a.flags & QS_FLAG_AUTORESET_SAME_STEP) && env_done;
+            if (same_step) {
+                // terminal observation head goes straight to final_obs (rare path, strided store is fine)
+                if (a.io.final_obs) {
+                    float* f = a.io.final_obs + i * a.obs_dim;
+                    f[0] = (float)d.px; f[1] = (float)d.py; f[2] = (float)d.pz;
+                    f[3] = (float)o.roll; f[4] = (float)o.pitch; f[5] = (float)o.yaw;
+                    f[6] = (float)d.vx; f[7] = (float)d.vy; f[8] = (float)d.vz;
+                    f[9] = (float)o.ax; f[10] = (float)o.ay; f[11] = (float)o.az;
+                    mode |= 2;
+                }
+                if (a.flags & QS_FLAG_AUTORESET_CLEARS_HISTORY) mode |= 4;
+                if (a.flags & QS_FLAG_AUTORESET_CLEARS_PID) pst = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                init_drone(a.st, tbl, d);                                          // BaseAviary.py:451-505
+                double Rr[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+                if (a.flags & QS_FLAG_RPY_F32) qs::derive<true>(d, Rr, o); else qs::derive<false>(d, Rr, o);
+                rpm[0] = rpm[1] = rpm[2] = rpm[3] = 0.0;                           // last_clipped_action = 0
+                sc = -a.counter_inc;                                               // -> 0 after the increment below
+            }
+            // KIN observation head: pos3 rpy3 vel3 ang_v3 (BaseRLAviary.py:310-315)
+            h[0] = (float)d.px; h[1] = (float)d.py; h[2] = (float)d.pz;
+            h[3] = (float)o.roll; h[4] = (float)o.pitch; h[5] = (float)o.yaw;
+            h[6] = (float)d.vx; h[7] = (float)d.vy; h[8] = (float)d.vz;
+            h[9] = (float)o.ax; h[10] = (float)o.ay; h[11] = (float)o.az;
+            act_s[4 * t] = act[0]; act_s[4 * t + 1] = act[1]; act_s[4 * t + 2] = act[2]; act_s[4 * t + 3] = act[3];
+        }
+        mode_s[t] = mode;
+        store_drone(a.st.planes, N, i, d);
+        if (a.st.last_rpm && !pending)
+            st4(a.st.last_rpm, i, make_float4((float)rpm[0], (float)rpm[1], (float)rpm[2], (float)rpm[3]));
+        if (pid_act) {
+            float* ps = a.st.pid;
+            ps[i] = (float)pst.ipx; ps[N + i] = (float)pst.ipy; ps[2 * N + i] = (float)pst.ipz;
+            ps[3 * N + i] = (float)pst.lr; ps[4 * N + i] = (float)pst.lp; ps[5 * N + i] = (float)pst.ly;
+            ps[6 * N + i] = (float)pst.irx; ps[7 * N + i] = (float)pst.iry; ps[8 * N + i] = (float)pst.irz;
+        }
+        if (dslot == 0 && want_epilogue) {
+            if (pending) {
+                a.st.step_counter[e] = 0;
+                a.st.pending_reset[e] = 0;
+            } else {
+                a.st.step_counter[e] = sc + a.counter_inc;                         // BaseAviary.py:382
+                if ((a.flags & QS_FLAG_AUTORESET_NEXT_STEP) && a.st.pending_reset && env_done) a.st.pending_reset[e] = 1;
+            }
+        }
+    }
+    if (a.io.obs == nullptr || !want_epilogue) return;
+    __syncthreads();
+
+    // ---- cooperative, coalesced write of this CTA's observation rows --------------------------------------
+    const int rows = (int)((N - c0) < tpb ? (N - c0) : tpb);
+    if (RAW) {
+        float* out = a.io.obs + c0 * 20;
+        for (int j = t; j < rows * 20; j += blockDim.x) out[j] = head_s[j];
+    } else {
+        const int od = a.obs_dim;
+        const int hist_end = od - A;                       // columns [12, hist_end) come from prev columns [12+A, od)
+        const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+        for (int r = warp; r < rows; r += nwarps) {
+            const long long row = (c0 + r) * (long long)od;
+            const unsigned char mode = mode_s[r];
+            const bool keep = mode & 1;
+            const int shift = keep ? 0 : A;
+            for (int c = lane; c < od; c += 32) {
+                float v;
+                if (c < 12) {
+                    v = head_s[r * 12 + c];
+                } else {
+                    if (c < hist_end || keep) v = __ldg(a.io.obs_prev + row + c + shift);
+                    else v = act_s[4 * r + (c - hist_end)];
+                    if (mode & 2) a.io.final_obs[row + c] = v;
+                    if (mode & 4) v = 0.f;
+                }
+                a.io.obs[row + c] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DSLPIDControl.computeControl for n drones (stand-alone entry).
+// ---------------------------------------------------------------------------------------------------------
+struct PidArgs {
+    QsParams P;
+    float* pid;
+    double dt;
+    const float *pos, *quat, *vel, *tpos, *trpy, *tvel, *trr;
+    int pos_stride, quat_stride, vel_stride, n;
+    float *rpm_out, *pos_e_out, *yaw_e_out;
+};
+
+__global__ void __launch_bounds__(128) pid_kernel(const __grid_constant__ PidArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long N = a.n;
+    if (i >= N) return;
+    const float* p = a.pos + i * a.pos_stride;
+    const float* q = a.quat + i * a.quat_stride;
+    const float* v = a.vel + i * a.vel_stride;
+    qs::PidState st;
+    st.ipx = a.pid[i]; st.ipy = a.pid[N + i]; st.ipz = a.pid[2 * N + i];
+    st.lr = a.pid[3 * N + i]; st.lp = a.pid[4 * N + i]; st.ly = a.pid[5 * N + i];
+    st.irx = a.pid[6 * N + i]; st.iry = a.pid[7 * N + i]; st.irz = a.pid[8 * N + i];
+    const double tyaw = a.trpy ? (double)a.trpy[3 * i + 2] : 0.0;
+    double tv[3] = {0, 0, 0}, tr[3] = {0, 0, 0};
+    if (a.tvel) { tv[0] = a.tvel[3 * i]; tv[1] = a.tvel[3 * i + 1]; tv[2] = a.tvel[3 * i + 2]; }
+    if (a.trr) { tr[0] = a.trr[3 * i]; tr[1] = a.trr[3 * i + 1]; tr[2] = a.trr[3 * i + 2]; }
+    double rpm[4], pe[3], ye;
+    qs::pid_control(a.P, st, a.dt, p[0], p[1], p[2], q[0], q[1], q[2], q[3], v[0], v[1], v[2],
+                    a.tpos[3 * i], a.tpos[3 * i + 1], a.tpos[3 * i + 2], tyaw, tv[0], tv[1], tv[2], tr[0], tr[1], tr[2],
+                    rpm, pe, ye);
+    a.pid[i] = (float)st.ipx; a.pid[N + i] = (float)st.ipy; a.pid[2 * N + i] = (float)st.ipz;
+    a.pid[3 * N + i] = (float)st.lr; a.pid[4 * N + i] = (float)st.lp; a.pid[5 * N + i] = (float)st.ly;
+    a.pid[6 * N + i] = (float)st.irx; a.pid[7 * N + i] = (float)st.iry; a.pid[8 * N + i] = (float)st.irz;
+    reinterpret_cast<float4*>(a.rpm_out)[i] = make_float4((float)rpm[0], (float)rpm[1], (float)rpm[2], (float)rpm[3]);
+    if (a.pos_e_out) { a.pos_e_out[3 * i] = (float)pe[0]; a.pos_e_out[3 * i + 1] = (float)pe[1]; a.pos_e_out[3 * i + 2] = (float)pe[2]; }
+    if (a.yaw_e_out) a.yaw_e_out[i] = (float)ye;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pairwise downwash for large aviaries: classic tiled all-pairs.  Block = 256 drones of ONE aviary; the
+// aviary's positions stream through shared memory in tiles of 256.  The pair term is evaluated in float32
+// (predicate first, expf only for pairs in range), the sum is accumulated in float64.
+// ---------------------------------------------------------------------------------------------------------
+struct DwArgs {
+    float prop_radius, dw1, dw2, dw3;
+    const float* planes;
+    float* fz;
+    int D, tiles_per_env;
+    long long N;
+};
+
+__global__ void __launch_bounds__(256) downwash_kernel(const __grid_constant__ DwArgs a) {
+    __shared__ float4 tile[256];
+    const int env = blockIdx.x / a.tiles_per_env;
+    const int tb = blockIdx.x - env * a.tiles_per_env;
+    const long long base = (long long)env * a.D;
+    const int n = tb * 256 + threadIdx.x;                 // my drone inside the aviary
+    const bool live = n < a.D;
+    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) me = ldg4(a.planes, base + n);
+    double acc = 0.0;
+    for (int j0 = 0; j0 < a.D; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        tile[threadIdx.x] = (j < a.D) ? ldg4(a.planes, base + j) : make_float4(0.f, 0.f, -1e30f, 0.f);
+        __syncthreads();
+        const int cnt = min(256, a.D - j0);
+        float part = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < cnt; ++k) {
+            const float4 o = tile[k];
+            const float dz = o.z - me.z;
+            const float dx = o.x - me.x, dy = o.y - me.y;
+            const float dxy2 = dx * dx + dy * dy;
+            if (dz > 0.f && dxy2 < 100.f) {                                    // BaseAviary.py:800
+                const float rr = a.prop_radius / (4.f * dz);
+                const float alpha = a.dw1 * (rr * rr);
+                const float beta = a.dw2 * dz + a.dw3;
+                const float u2 = dxy2 / (beta * beta);
+                part -= alpha * expf(-0.5f * u2);
+            }
+        }
+        acc += (double)part;
+        __syncthreads();
+    }
+    if (live) a.fz[base + n] = (float)acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Masked reset (BaseAviary.reset / _housekeeping).
+// ---------------------------------------------------------------------------------------------------------
+struct ResetArgs {
+    QsState st;
+    const unsigned char* mask;
+    int D, reset_pid, obs_dim, raw20;
+    long long N;
+    float* obs;
+};
+
+__global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ ResetArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const long long e = i / a.D;
+    if (a.mask && !a.mask[e]) return;
+    const int dslot = (int)(i - e * a.D);
+    const long long tbl = a.st.tables_per_env ? i : dslot;
+    qs::Drone d;
+    init_drone(a.st, tbl, d);
+    qs::Derived o;
+    const double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    qs::derive<false>(d, R, o);
+    store_drone(a.st.planes, a.N, i, d);
+    if (a.st.last_rpm) st4(a.st.last_rpm, i, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (a.reset_pid && a.st.pid)
+        for (int k = 0; k < 9; ++k) a.st.pid[k * a.N + i] = 0.f;
+    if (dslot == 0) {
+        a.st.step_counter[e] = 0;
+        if (a.st.pending_reset) a.st.pending_reset[e] = 0;
+    }
+    if (a.obs) {
+        if (a.raw20) {
+            float* h = a.obs + i * 20;
+            h[0] = (float)d.px; h[1] = (float)d.py; h[2] = (float)d.pz;
+            h[3] = (float)d.qx; h[4] = (float)d.qy; h[5] = (float)d.qz; h[6] = (float)d.qw;
+            h[7] = (float)o.roll; h[8] = (float)o.pitch; h[9] = (float)o.yaw;
+            for (int k = 10; k < 20; ++k) h[k] = 0.f;
+        } else {
+            float* h = a.obs + i * a.obs_dim;
+            h[0] = (float)d.px; h[1] = (float)d.py; h[2] = (float)d.pz;
+            h[3] = (float)o.roll; h[4] = (float)o.pitch; h[5] = (float)o.yaw;
+            for (int k = 6; k < 12; ++k) h[k] = 0.f;
+        }
+    }
+}
+
+size_t step_smem_bytes() {
+    return (size_t)kMaxTPB * 20 * 4 + (size_t)kMaxTPB * 4 * 4 + (size_t)kMaxTPB * 2 * 8 + (size_t)kMaxTPB * 3 * 8 + 3 * (size_t)kMaxTPB;
+}
+
+template <bool RAW>
+cudaError_t launch_step(const StepArgs& a, cudaStream_t s) {
+    const int blocks = (int)((a.N + a.tpb - 1) / a.tpb);
+    const int threads = ((a.tpb + 31) / 32) * 32;
+    const size_t sm = step_smem_bytes();
+#define QS_CASE(E) case E: step_kernel<E, RAW><<<blocks, threads, sm, s>>>(a); break;
+    switch (a.effects & 7u) {
+        QS_CASE(0) QS_CASE(1) QS_CASE(2) QS_CASE(3) QS_CASE(4) QS_CASE(5) QS_CASE(6) QS_CASE(7)
+    }
+#undef QS_CASE
+    return cudaGetLastError();
+}
+
+int act_width(int act_type) {
+    switch (act_type) {
+        case QS_ACT_RPM: case QS_ACT_VEL: case QS_ACT_RAW_RPM: return 4;
+        case QS_ACT_PID: return 3;
+        case QS_ACT_ONE_D_RPM: case QS_ACT_ONE_D_PID: return 1;
+        default: return -1;
+    }
+}
+
+int check_state(const QsState* st, int need_tables) {
+    if (!st || !st->planes || !st->step_counter) return fail(QS_ERR_NULL, "QsState: planes/step_counter is NULL");
+    if (!aligned16(st->planes)) return fail(QS_ERR_ALIGN, "QsState.planes must be 16-byte aligned");
+    if (st->last_rpm && !aligned16(st->last_rpm)) return fail(QS_ERR_ALIGN, "QsState.last_rpm must be 16-byte aligned");
+    if (need_tables) {
+        if (!st->init_pos || !st->init_quat) return fail(QS_ERR_NULL, "QsState: init_pos/init_quat is NULL");
+        if (!aligned16(st->init_pos) || !aligned16(st->init_quat)) return fail(QS_ERR_ALIGN, "init tables must be 16-byte aligned");
+    }
+    return 0;
+}
+
+int block_size_for(int D) { return D <= kMaxTPB ? D * (kMaxTPB / D) : kMaxTPB; }
+
+}  // namespace
+
+// =============================================================================================================
+extern "C" {
+
+int qs_abi_version(void) { return QS_ABI_VERSION; }
+const char* qs_last_error(void) { return g_err; }
+int qs_sizeof_params(void) { return (int)sizeof(QsParams); }
+int qs_sizeof_state(void) { return (int)sizeof(QsState); }
+int qs_sizeof_step_io(void) { return (int)sizeof(QsStepIO); }
+
+int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_type, int task,
+            int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream) {
+    if (!p || !io) return fail(QS_ERR_NULL, "qs_step: NULL params/io");
+    const bool autoreset = flags & (QS_FLAG_AUTORESET_SAME_STEP | QS_FLAG_AUTORESET_NEXT_STEP);
+    if (int rc = check_state(st, autoreset ? 1 : 0)) return rc;
+    if (n_envs <= 0 || drones_per_env <= 0 || substeps <= 0) return fail(QS_ERR_SIZE, "qs_step: n_envs, drones_per_env, substeps must be > 0");
+    const int A = act_width(act_type);
+    if (A < 0 || act_type == QS_ACT_RAW_RPM) return fail(QS_ERR_ENUM, "qs_step: bad act_type (use qs_dyn_substeps for raw rpm)");
+    if (task != QS_TASK_NONE && task != QS_TASK_HOVER) return fail(QS_ERR_ENUM, "qs_step: bad task");
+    if (effects & ~7u) return fail(QS_ERR_ENUM, "qs_step: bad effects");
+    if ((flags & QS_FLAG_AUTORESET_SAME_STEP) && (flags & QS_FLAG_AUTORESET_NEXT_STEP)) return fail(QS_ERR_ENUM, "qs_step: two autoreset modes");
+    if (!io->action) return fail(QS_ERR_NULL, "qs_step: action is NULL");
+    if (A == 4 && !aligned16(io->action)) return fail(QS_ERR_ALIGN, "qs_step: [N][4] action must be 16-byte aligned");
+    const bool skip = flags & QS_FLAG_SKIP_EPILOGUE;
+    if ((flags & QS_FLAG_RPM_FROM_LAST) && !st->last_rpm) return fail(QS_ERR_NULL, "qs_step: RPM_FROM_LAST needs QsState.last_rpm");
+    if (!skip && (!io->reward || !io->terminated || !io->truncated)) return fail(QS_ERR_NULL, "qs_step: reward/terminated/truncated is NULL");
+    if (io->act_buffer_size < 0) return fail(QS_ERR_SIZE, "qs_step: act_buffer_size < 0");
+    if (io->obs && io->act_buffer_size > 0 && !io->obs_prev) return fail(QS_ERR_NULL, "qs_step: obs_prev is NULL");
+    if (io->obs && io->obs == io->obs_prev) return fail(QS_ERR_UNSUPPORTED, "qs_step: obs and obs_prev must be distinct buffers");
+    if (task == QS_TASK_HOVER && !st->target_pos) return fail(QS_ERR_NULL, "qs_step: target_pos is NULL");
+    if (task == QS_TASK_HOVER && !aligned16(st->target_pos)) return fail(QS_ERR_ALIGN, "qs_step: target_pos must be 16-byte aligned");
+    if (task == QS_TASK_HOVER && drones_per_env > kMaxTPB) return fail(QS_ERR_UNSUPPORTED, "qs_step: task reduction supports drones_per_env <= 128");
+    const bool pid_act = act_type == QS_ACT_PID || act_type == QS_ACT_VEL || act_type == QS_ACT_ONE_D_PID;
+    if (pid_act && !st->pid) return fail(QS_ERR_NULL, "qs_step: PID action type needs QsState.pid");
+    if ((effects & QS_EFFECT_DRAG) && !st->last_rpm) return fail(QS_ERR_NULL, "qs_step: DRAG needs QsState.last_rpm");
+    if ((effects & QS_EFFECT_DW) && !io->dw_fz && drones_per_env > kMaxTPB)
+        return fail(QS_ERR_UNSUPPORTED, "qs_step: in-CTA downwash needs drones_per_env <= 128 (else pass dw_fz from qs_downwash, substeps = 1)");
+    if ((effects & QS_EFFECT_DW) && io->dw_fz && substeps != 1) return fail(QS_ERR_UNSUPPORTED, "qs_step: external dw_fz requires substeps == 1");
+    if ((flags & QS_FLAG_AUTORESET_NEXT_STEP) && !st->pending_reset) return fail(QS_ERR_NULL, "qs_step: NEXT_STEP autoreset needs pending_reset");
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = *p; a.st = *st; a.io = *io;
+    a.act_type = act_type; a.task = task; a.n_envs = n_envs; a.D = drones_per_env; a.substeps = substeps;
+    a.N = n_envs * drones_per_env; a.A = A; a.obs_dim = 12 + io->act_buffer_size * A;
+    a.tpb = block_size_for(drones_per_env);
+    a.counter_inc = io->tick_substeps > 0 ? io->tick_substeps : substeps;
+    a.effects = effects; a.flags = flags;
+    const cudaError_t e = launch_step<false>(a, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "qs_step launch");
+}
+
+int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, float* state20_out, const float* dw_fz,
+                    int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream) {
+    if (!p || !rpm) return fail(QS_ERR_NULL, "qs_dyn_substeps: NULL params/rpm");
+    if (int rc = check_state(st, 0)) return rc;
+    if (n_envs <= 0 || drones_per_env <= 0 || substeps <= 0) return fail(QS_ERR_SIZE, "qs_dyn_substeps: sizes must be > 0");
+    if (!aligned16(rpm)) return fail(QS_ERR_ALIGN, "qs_dyn_substeps: rpm must be 16-byte aligned");
+    if (effects & ~7u) return fail(QS_ERR_ENUM, "qs_dyn_substeps: bad effects");
+    if ((effects & QS_EFFECT_DRAG) && !st->last_rpm) return fail(QS_ERR_NULL, "qs_dyn_substeps: DRAG needs QsState.last_rpm");
+    if ((effects & QS_EFFECT_DW) && !dw_fz && drones_per_env > kMaxTPB)
+        return fail(QS_ERR_UNSUPPORTED, "qs_dyn_substeps: in-CTA downwash needs drones_per_env <= 128 (else pass dw_fz, substeps = 1)");
+    if ((effects & QS_EFFECT_DW) && dw_fz && substeps != 1) return fail(QS_ERR_UNSUPPORTED, "qs_dyn_substeps: external dw_fz requires substeps == 1");
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = *p; a.st = *st;
+    a.io.action = rpm; a.io.obs = state20_out; a.io.dw_fz = dw_fz;
+    a.act_type = QS_ACT_RAW_RPM; a.task = QS_TASK_NONE; a.n_envs = n_envs; a.D = drones_per_env; a.substeps = substeps;
+    a.N = n_envs * drones_per_env; a.A = 4; a.obs_dim = 20;
+    a.tpb = block_size_for(drones_per_env);
+    a.counter_inc = substeps;
+    a.effects = effects; a.flags = flags & QS_FLAG_RPY_F32;
+    const cudaError_t e = launch_step<true>(a, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "qs_dyn_substeps launch");
+}
+
+int qs_pid_control(const QsParams* p, float* pid_state, double control_timestep,
+                   const float* cur_pos, int pos_stride, const float* cur_quat, int quat_stride,
+                   const float* cur_vel, int vel_stride,
+                   const float* target_pos, const float* target_rpy, const float* target_vel, const float* target_rpy_rates,
+                   int n, float* rpm_out, float* pos_e_out, float* yaw_e_out, void* stream) {
+    if (!p || !pid_state || !cur_pos || !cur_quat || !cur_vel || !target_pos || !rpm_out) return fail(QS_ERR_NULL, "qs_pid_control: NULL argument");
+    if (n <= 0 || pos_stride < 3 || quat_stride < 4 || vel_stride < 3) return fail(QS_ERR_SIZE, "qs_pid_control: bad n/stride");
+    if (!(control_timestep > 0.0)) return fail(QS_ERR_SIZE, "qs_pid_control: control_timestep must be > 0");
+    if (!aligned16(rpm_out)) return fail(QS_ERR_ALIGN, "qs_pid_control: rpm_out must be 16-byte aligned");
+    PidArgs a;
+    a.P = *p; a.pid = pid_state; a.dt = control_timestep;
+    a.pos = cur_pos; a.quat = cur_quat; a.vel = cur_vel; a.tpos = target_pos; a.trpy = target_rpy; a.tvel = target_vel; a.trr = target_rpy_rates;
+    a.pos_stride = pos_stride; a.quat_stride = quat_stride; a.vel_stride = vel_stride; a.n = n;
+    a.rpm_out = rpm_out; a.pos_e_out = pos_e_out; a.yaw_e_out = yaw_e_out;
+    pid_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "qs_pid_control launch");
+}
+
+int qs_downwash(const QsParams* p, const QsState* st, int n_envs, int drones_per_env, float* fz_out, void* stream) {
+    if (!p || !st || !st->planes || !fz_out) return fail(QS_ERR_NULL, "qs_downwash: NULL argument");
+    if (!aligned16(st->planes)) return fail(QS_ERR_ALIGN, "qs_downwash: planes must be 16-byte aligned");
+    if (n_envs <= 0 || drones_per_env <= 0) return fail(QS_ERR_SIZE, "qs_downwash: sizes must be > 0");
+    DwArgs a;
+    a.prop_radius = (float)p->prop_radius; a.dw1 = (float)p->dw_coeff[0]; a.dw2 = (float)p->dw_coeff[1]; a.dw3 = (float)p->dw_coeff[2];
+    a.planes = st->planes; a.fz = fz_out; a.D = drones_per_env; a.tiles_per_env = (drones_per_env + 255) / 256;
+    a.N = (long long)n_envs * drones_per_env;
+    downwash_kernel<<<n_envs * a.tiles_per_env, 256, 0, (cudaStream_t)stream>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "qs_downwash launch");
+}
+
+int qs_reset(const QsParams* p, const QsState* st, const unsigned char* mask, int n_envs, int drones_per_env,
+             int reset_pid, float* obs, int obs_dim, int raw_state20, void* stream) {
+    (void)p;
+    if (int rc = check_state(st, 1)) return rc;
+    if (n_envs <= 0 || drones_per_env <= 0) return fail(QS_ERR_SIZE, "qs_reset: sizes must be > 0");
+    if (obs && !raw_state20 && obs_dim < 12) return fail(QS_ERR_SIZE, "qs_reset: obs_dim < 12");
+    ResetArgs a;
+    a.st = *st; a.mask = mask; a.D = drones_per_env; a.reset_pid = reset_pid; a.obs_dim = obs_dim; a.raw20 = raw_state20;
+    a.N = (long long)n_envs * drones_per_env; a.obs = obs;
+    reset_kernel<<<(int)((a.N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "qs_reset launch");
+}
+
+}  // extern "C"

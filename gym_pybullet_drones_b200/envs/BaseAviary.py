@@ -1,0 +1,520 @@
+"""B200-native base aviary: E independent aviaries of D drones stepped in lockstep on one GPU.
+
+Keeps the constructor, attribute names, template-method hooks and reset/step
+surface of the reference's `BaseAviary` (gym_pybullet_drones/envs/BaseAviary.py:25-383)
+but owns no PyBullet client: the per-drone state is a structure of arrays of
+float32 CUDA tensors and `step()` is one call into the C-ABI CUDA library
+(include/quadsim.h).  Every `Physics` member runs the explicit `Physics.DYN`
+model (BaseAviary.py:815-892); the PYB_* members switch on the corresponding
+DYN+ aerodynamic terms.
+
+Two calling conventions, chosen by `num_envs`:
+  * `num_envs=None` (default): a single aviary with the reference's gymnasium `Env`
+    API -- `reset() -> (obs[D, ...] ndarray, info)`, `step(action[D, A]) -> (obs, float,
+    bool, bool, info)` -- so `examples/learn.py`, `pid.py` style code runs unchanged.
+  * `num_envs=E`: gymnasium `VectorEnv`-style API over E aviaries -- `reset() ->
+    (obs[E, D, ...], infos)`, `step(actions[E, D, A]) -> (obs, rewards[E],
+    terminations[E], truncations[E], infos)` with torch CUDA tensors in/out (zero
+    copy) or NumPy arrays in/out (pinned staging buffers).
+"""
+import ctypes as C
+import warnings
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from .._compat import (AUTORESET_DISABLED, AUTORESET_NEXT_STEP, AUTORESET_SAME_STEP, Env, batch_box, spaces)
+from ..params import AviaryConstants, fill_params, quaternion_from_euler
+from ..utils.enums import DroneModel, Physics
+
+_PHYSICS_EFFECTS = {
+    Physics.PYB: 0, Physics.DYN: 0,
+    Physics.PYB_GND: N.EFFECT_GND, Physics.PYB_DRAG: N.EFFECT_DRAG, Physics.PYB_DW: N.EFFECT_DW,
+    Physics.PYB_GND_DRAG_DW: N.EFFECT_GND | N.EFFECT_DRAG | N.EFFECT_DW,
+}
+
+_AUTORESET = {None: 0, "disabled": 0, AUTORESET_DISABLED: 0,
+              "next_step": N.FLAG_AUTORESET_NEXT_STEP, AUTORESET_NEXT_STEP: N.FLAG_AUTORESET_NEXT_STEP,
+              "same_step": N.FLAG_AUTORESET_SAME_STEP, AUTORESET_SAME_STEP: N.FLAG_AUTORESET_SAME_STEP}
+
+
+class BaseAviary(Env):
+    """Base class for the GPU aviaries (reference: envs/BaseAviary.py:19)."""
+
+    metadata = {"render_modes": []}
+
+    ################################################################################
+
+    def __init__(self,
+                 drone_model: DroneModel = DroneModel.CF2X,
+                 num_drones: int = 1,
+                 neighbourhood_radius: float = np.inf,
+                 initial_xyzs=None,
+                 initial_rpys=None,
+                 physics: Physics = Physics.PYB,
+                 pyb_freq: int = 240,
+                 ctrl_freq: int = 240,
+                 gui=False,
+                 record=False,
+                 obstacles=False,
+                 user_debug_gui=True,
+                 vision_attributes=False,
+                 output_folder='results',
+                 *,
+                 num_envs=None,
+                 device=None,
+                 autoreset=None,
+                 autoreset_clears_controllers=False,
+                 autoreset_clears_action_buffer=False,
+                 rpy_f32=False,
+                 host_copy=True,
+                 ):
+        """Same positional/keyword parameters as the reference (BaseAviary.py:25-40).
+
+        Keyword-only extensions
+        -----------------------
+        num_envs : int | None
+            None = single aviary with the reference's Env API; E = vectorised API over E aviaries.
+        device : torch.device | str | int | None
+            CUDA device holding the state (default: the current CUDA device).
+        autoreset : None | "next_step" | "same_step" | "disabled"
+            Vector-env autoreset mode (gymnasium's AutoresetMode members are accepted too).
+        autoreset_clears_controllers, autoreset_clears_action_buffer : bool
+            The reference's reset() clears neither the embedded PID controllers nor the action
+            buffer (quirk kept by default); set to clear them when an env auto-resets.
+        rpy_f32 : bool
+            Evaluate the reported roll/pitch/yaw with float32 atan2/asin (faster, ~2e-7 rad).
+        host_copy : bool
+            NumPy mode only: return fresh arrays (True) or views of the pinned staging buffers
+            that stay valid until the next-but-one step (False).
+        """
+        if not torch.cuda.is_available():
+            raise RuntimeError("gym_pybullet_drones_b200 needs a CUDA device: the simulator has no CPU path")
+        self._lib = N.lib()
+        if gui or record:
+            warnings.warn("gui/record are not available on the GPU simulator (no renderer); ignored")
+        if vision_attributes:
+            raise NotImplementedError("RGB observations need PyBullet's renderer; only ObservationType.KIN is supported")
+        #### Constants (BaseAviary.py:74-128) ######################
+        c = AviaryConstants(drone_model, pyb_freq, ctrl_freq)
+        self.__dict__.update(vars(c))
+        self._consts = c
+        #### Parameters / options ##################################
+        self.NUM_DRONES = int(num_drones)
+        self.NEIGHBOURHOOD_RADIUS = neighbourhood_radius
+        self.GUI, self.RECORD, self.PHYSICS = False, False, physics
+        self.OBSTACLES, self.USER_DEBUG, self.OUTPUT_FOLDER = obstacles, user_debug_gui, output_folder
+        self.VISION_ATTR = False
+        self.VECTORIZED = num_envs is not None
+        self.num_envs = int(num_envs) if self.VECTORIZED else 1
+        if self.num_envs <= 0 or self.NUM_DRONES <= 0:
+            raise ValueError("num_envs and num_drones must be positive")
+        self._E, self._D = self.num_envs, self.NUM_DRONES
+        self._N = self._E * self._D
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._effects = _PHYSICS_EFFECTS[physics]
+        if autoreset not in _AUTORESET:
+            raise ValueError("autoreset must be None, 'next_step', 'same_step' or 'disabled'")
+        self._flags = _AUTORESET[autoreset]
+        if autoreset_clears_controllers:
+            self._flags |= N.FLAG_AUTORESET_CLEARS_PID
+        if autoreset_clears_action_buffer:
+            self._flags |= N.FLAG_AUTORESET_CLEARS_HISTORY
+        if rpy_f32:
+            self._flags |= N.FLAG_RPY_F32
+        self.autoreset_mode = {0: AUTORESET_DISABLED, N.FLAG_AUTORESET_NEXT_STEP: AUTORESET_NEXT_STEP,
+                               N.FLAG_AUTORESET_SAME_STEP: AUTORESET_SAME_STEP}[_AUTORESET[autoreset]]
+        self.metadata = dict(self.metadata, autoreset_mode=self.autoreset_mode)
+        self._host_copy = host_copy
+        #### Initial poses (BaseAviary.py:194-207); [D,3] shared by all aviaries or [E,D,3] per aviary ####
+        self._tables_per_env = False
+        if initial_xyzs is None:
+            self.INIT_XYZS = c.default_init_xyzs(self.NUM_DRONES)
+        else:
+            self.INIT_XYZS = self._check_init(initial_xyzs, "initial_xyzs")
+        if initial_rpys is None:
+            self.INIT_RPYS = np.zeros((self.NUM_DRONES, 3))
+        else:
+            self.INIT_RPYS = self._check_init(initial_rpys, "initial_rpys")
+        #### Action/observation spaces (hooks of the subclasses) ####
+        self.action_space = self._actionSpace()
+        self.observation_space = self._observationSpace()
+        if self.VECTORIZED:
+            self.single_action_space, self.single_observation_space = self.action_space, self.observation_space
+            self.action_space = batch_box(self.single_action_space, self._E)
+            self.observation_space = batch_box(self.single_observation_space, self._E)
+        #### Device state ##########################################
+        self._allocate()
+        self._housekeeping()
+
+    ################################################################################
+    # configuration supplied by subclasses
+
+    def _act_type(self):
+        """QS_ACT_* of this env (RAW_RPM for CtrlAviary-style envs)."""
+        raise NotImplementedError
+
+    def _task(self):
+        return N.TASK_NONE
+
+    def _act_width(self):
+        return 4
+
+    def _act_buffer_size(self):
+        return 0
+
+    def _task_params(self):
+        """dict(xy_bound=..., episode_len_sec=...) overrides for QsParams."""
+        return {}
+
+    def _target_table(self):
+        """[D,3] / [E,D,3] TARGET_POS or None."""
+        return None
+
+    ################################################################################
+
+    def _check_init(self, arr, name):
+        a = np.asarray(arr, dtype=np.float64)
+        if a.shape == (self.NUM_DRONES, 3):
+            return a
+        if a.shape == (self._E, self.NUM_DRONES, 3) and self.VECTORIZED:
+            self._tables_per_env = True
+            return a
+        raise ValueError("[ERROR] invalid %s in BaseAviary.__init__(), try %s.reshape(NUM_DRONES,3)" % (name, name))
+
+    def _table(self, arr, width=3):
+        """[D,w] or [E,D,w] float64 -> float32 device table [rows,4] (16-byte rows)."""
+        a = np.asarray(arr, dtype=np.float64)
+        if self._tables_per_env:
+            a = np.broadcast_to(a, (self._E, self._D, a.shape[-1])).reshape(self._N, a.shape[-1])
+        else:
+            a = a.reshape(self._D, a.shape[-1])
+        out = np.zeros((a.shape[0], 4), np.float32)
+        out[:, :a.shape[1]] = a
+        return torch.from_numpy(out).to(self.device)
+
+    def _allocate(self):
+        dev, E, D, n = self.device, self._E, self._D, self._N
+        self._A = self._act_width()
+        self._B = self._act_buffer_size()
+        raw = self._act_type() == N.ACT_RAW_RPM
+        self._obs_dim = 20 if raw else 12 + self._B * self._A
+        f32 = dict(dtype=torch.float32, device=dev)
+        self._planes = torch.zeros((4, n, 4), **f32)
+        self._last_rpm = torch.zeros((n, 4), **f32)
+        self._step_counter = torch.zeros((E,), dtype=torch.int32, device=dev)
+        self._pending = torch.zeros((E,), dtype=torch.uint8, device=dev)
+        needs_pid = self._act_type() in (N.ACT_PID, N.ACT_VEL, N.ACT_ONE_D_PID)
+        self._pid = torch.zeros((9, n), **f32) if needs_pid else None
+        self._obs_buf = [torch.zeros((n, self._obs_dim), **f32), torch.zeros((n, self._obs_dim), **f32)]
+        self._cur = 0
+        self._reward = torch.zeros((E,), **f32)
+        self._terminated = torch.zeros((E,), dtype=torch.bool, device=dev)
+        self._truncated = torch.zeros((E,), dtype=torch.bool, device=dev)
+        self._final_obs = torch.zeros((n, self._obs_dim), **f32) if (self._flags & N.FLAG_AUTORESET_SAME_STEP) else None
+        big_dw = (self._effects & N.EFFECT_DW) and D > 128
+        self._dw_fz = torch.zeros((n,), **f32) if big_dw else None
+        self._action_dev = torch.zeros((n, self._A), **f32)
+        #### tables ####
+        if np.asarray(self.INIT_XYZS).ndim != np.asarray(self.INIT_RPYS).ndim and self._tables_per_env:
+            pass  # _table() broadcasts the [D,3] one
+        self._init_pos = self._table(self.INIT_XYZS)
+        self._init_quat = self._table(quaternion_from_euler(self.INIT_RPYS), 4)
+        tt = self._target_table()
+        self._target = self._table(tt) if tt is not None else None
+        #### C structs (pointers are stable: tensors are never reallocated) ####
+        tp = dict(episode_len_sec=float(getattr(self, "EPISODE_LEN_SEC", 8)))
+        tp.update(self._task_params())
+        self._P = fill_params(self._consts, **tp)
+        st = N.QsState()
+        st.planes, st.last_rpm = self._planes.data_ptr(), self._last_rpm.data_ptr()
+        st.step_counter, st.pending_reset = self._step_counter.data_ptr(), self._pending.data_ptr()
+        st.pid = self._pid.data_ptr() if self._pid is not None else None
+        st.init_pos, st.init_quat = self._init_pos.data_ptr(), self._init_quat.data_ptr()
+        st.target_pos = self._target.data_ptr() if self._target is not None else None
+        st.tables_per_env = 1 if self._tables_per_env else 0
+        self._st = st
+        io = N.QsStepIO()
+        io.reward, io.terminated, io.truncated = self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr()
+        io.final_obs = self._final_obs.data_ptr() if self._final_obs is not None else None
+        io.dw_fz = self._dw_fz.data_ptr() if self._dw_fz is not None else None
+        io.act_buffer_size = self._B
+        io.tick_substeps = 0
+        self._io = io
+        #### pinned host staging for the NumPy API ####
+        self._h_action = torch.zeros((n, self._A), dtype=torch.float32).pin_memory()
+        self._h_obs = [torch.zeros((n, self._obs_dim), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._h_reward = [torch.zeros((E,), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._h_term = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
+        self._h_trunc = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
+        self._h_final = torch.zeros((n, self._obs_dim), dtype=torch.float32).pin_memory() if self._final_obs is not None else None
+        self._hcur = 0
+
+    ################################################################################
+    # state views (float32 CUDA tensors; names follow BaseAviary.py:470-476)
+
+    @property
+    def pos(self):
+        return self._planes[0, :, 0:3].view(self._E, self._D, 3) if self.VECTORIZED else self._host(self._planes[0, :, 0:3])
+
+    @property
+    def quat(self):
+        return self._planes[1].view(self._E, self._D, 4) if self.VECTORIZED else self._host(self._planes[1])
+
+    @property
+    def vel(self):
+        return self._planes[2, :, 0:3].view(self._E, self._D, 3) if self.VECTORIZED else self._host(self._planes[2, :, 0:3])
+
+    @property
+    def rpy_rates(self):
+        w = torch.stack([self._planes[0, :, 3].double() + self._planes[3, :, 1].double(),
+                         self._planes[2, :, 3].double() + self._planes[3, :, 2].double(),
+                         self._planes[3, :, 0].double() + self._planes[3, :, 3].double()], dim=1)
+        return w.view(self._E, self._D, 3) if self.VECTORIZED else w.cpu().numpy()
+
+    @property
+    def step_counter(self):
+        return self._step_counter if self.VECTORIZED else int(self._step_counter[0].item())
+
+    @property
+    def last_clipped_action(self):
+        return self._last_rpm.view(self._E, self._D, 4) if self.VECTORIZED else self._host(self._last_rpm)
+
+    @staticmethod
+    def _host(t):
+        return t.detach().cpu().numpy().astype(np.float64)
+
+    def set_state(self, pos=None, quat=None, vel=None, rpy_rates=None, step_counter=None):
+        """Overwrites (parts of) the kinematic state; arrays are [E,D,k] / [D,k] (any float dtype).
+        `rpy_rates` given as float64 keeps its extended precision."""
+        def dev(a, k):
+            return torch.as_tensor(np.asarray(a, dtype=np.float64).reshape(self._N, k), device=self.device)
+        if pos is not None:
+            self._planes[0, :, 0:3] = dev(pos, 3).float()
+        if quat is not None:
+            self._planes[1] = dev(quat, 4).float()
+        if vel is not None:
+            self._planes[2, :, 0:3] = dev(vel, 3).float()
+        if rpy_rates is not None:
+            w = dev(rpy_rates, 3)
+            hi = w.float()
+            lo = (w - hi.double()).float()
+            self._planes[0, :, 3], self._planes[2, :, 3], self._planes[3, :, 0] = hi[:, 0], hi[:, 1], hi[:, 2]
+            self._planes[3, :, 1], self._planes[3, :, 2], self._planes[3, :, 3] = lo[:, 0], lo[:, 1], lo[:, 2]
+        if step_counter is not None:
+            self._step_counter[:] = torch.as_tensor(np.broadcast_to(np.asarray(step_counter), (self._E,)).astype(np.int32), device=self.device)
+
+    ################################################################################
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _on_device(self):
+        return torch.cuda.device(self.device)
+
+    def _housekeeping(self, mask=None):
+        """BaseAviary._housekeeping (BaseAviary.py:451-505): counters, poses, velocities, rates, last action."""
+        with self._on_device():
+            raw = self._act_type() == N.ACT_RAW_RPM
+            m = None if mask is None else mask.data_ptr()
+            rc = self._lib.qs_reset(C.byref(self._P), C.byref(self._st), m, self._E, self._D, 0,
+                                    self._obs_buf[self._cur].data_ptr(), self._obs_dim, 1 if raw else 0, self._stream())
+        N.check(rc, "qs_reset")
+
+    def reset(self, seed: int = None, options: dict = None):
+        """Resets the environment(s) (BaseAviary.py:220-255).  Deterministic like the reference: `seed` only
+        seeds `np_random`.  options: {"reset_mask": bool[E]} restricts the reset to some aviaries (vector API);
+        {"reset_controllers": True} / {"reset_action_buffer": True} also clear what the reference leaves alone."""
+        super().reset(seed=seed)
+        options = options or {}
+        mask = options.get("reset_mask")
+        mask_t = None
+        if mask is not None:
+            mask_t = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if mask_t.shape != (self._E,):
+                raise ValueError("reset_mask must have shape (num_envs,)")
+        self._housekeeping(mask_t)
+        if options.get("reset_controllers") and self._pid is not None:
+            if mask_t is None:
+                self._pid.zero_()
+            else:
+                self._pid.view(9, self._E, self._D)[:, mask_t.bool()] = 0
+        if options.get("reset_action_buffer") and self._B > 0:
+            o = self._obs_buf[self._cur].view(self._E, self._D, self._obs_dim)
+            if mask_t is None:
+                o[:, :, 12:] = 0
+            else:
+                o[mask_t.bool(), :, 12:] = 0
+        obs = self._obs_buf[self._cur]
+        if self.VECTORIZED:
+            return self._shape_obs(obs), {}
+        return self._obs_to_host_single(obs), self._computeInfo()
+
+    ################################################################################
+
+    def _launch(self, action_dev):
+        """One control tick on the device (BaseAviary.step, BaseAviary.py:259-383)."""
+        io, cur = self._io, self._cur
+        io.action = action_dev.data_ptr()
+        io.obs_prev = self._obs_buf[cur].data_ptr()
+        io.obs = self._obs_buf[1 - cur].data_ptr()
+        S = self.PYB_STEPS_PER_CTRL
+        stream = self._stream()
+        raw = self._act_type() == N.ACT_RAW_RPM
+        L = self._lib
+        if self._dw_fz is None:
+            if raw:
+                rc = L.qs_dyn_substeps(C.byref(self._P), C.byref(self._st), io.action, io.obs, None,
+                                       self._E, self._D, S, self._effects, self._flags, stream)
+            else:
+                rc = L.qs_step(C.byref(self._P), C.byref(self._st), C.byref(io), self._act_type(), self._task(),
+                               self._E, self._D, S, self._effects, self._flags, stream)
+            N.check(rc, "qs_step")
+        else:
+            # aviary larger than one CTA with downwash: positions couple the drones every substep
+            for s in range(S):
+                N.check(L.qs_downwash(C.byref(self._P), C.byref(self._st), self._E, self._D, self._dw_fz.data_ptr(), stream), "qs_downwash")
+                if raw:
+                    last = s == S - 1
+                    rpm_src = io.action if s == 0 else self._last_rpm.data_ptr()
+                    rc = L.qs_dyn_substeps(C.byref(self._P), C.byref(self._st), rpm_src, io.obs if last else None,
+                                           self._dw_fz.data_ptr(), self._E, self._D, 1, self._effects, self._flags, stream)
+                else:
+                    fl = self._flags | (N.FLAG_RPM_FROM_LAST if s > 0 else 0) | (N.FLAG_SKIP_EPILOGUE if s < S - 1 else 0)
+                    io.tick_substeps = S
+                    rc = L.qs_step(C.byref(self._P), C.byref(self._st), C.byref(io), self._act_type(), self._task(),
+                                   self._E, self._D, 1, self._effects, fl, stream)
+                N.check(rc, "qs_step(split)")
+        self._cur = 1 - cur
+        return self._obs_buf[self._cur]
+
+    def _shape_obs(self, obs):
+        return obs.view(self._E, self._D, self._obs_dim)
+
+    def _obs_to_host_single(self, obs):
+        return obs.detach().cpu().numpy().reshape(self._D, self._obs_dim)
+
+    def step(self, action):
+        """Advances every aviary by one control tick.
+
+        Vector API: `action` is a float32 CUDA tensor [E, D, A] (used in place) or an ndarray (copied through a
+        pinned buffer); returns tensors or ndarrays accordingly.  Single-env API: ndarray [D, A] in, the
+        reference's 5-tuple out (BaseAviary.py:262-290)."""
+        with self._on_device():
+            if isinstance(action, torch.Tensor):
+                a = action
+                if a.device != self.device or a.dtype != torch.float32:
+                    a = a.to(device=self.device, dtype=torch.float32)
+                a = a.reshape(self._N, self._A)
+                if not a.is_contiguous() or (a.data_ptr() & 15):
+                    self._action_dev.copy_(a)
+                    a = self._action_dev
+                obs = self._launch(a)
+                if not self.VECTORIZED:
+                    return self._single_result(obs)
+                info = {}
+                if self._final_obs is not None:
+                    info = {"final_obs": self._final_obs.view(self._E, self._D, self._obs_dim), "_final_obs": self._terminated | self._truncated}
+                return self._shape_obs(obs), self._reward, self._terminated, self._truncated, info
+            #### NumPy path: pinned H2D of the action, D2H of the results, all inside this call ####
+            a_np = np.asarray(action, dtype=np.float32).reshape(self._N, self._A)
+            self._h_action.numpy()[...] = a_np
+            self._action_dev.copy_(self._h_action, non_blocking=True)
+            obs = self._launch(self._action_dev)
+            if not self.VECTORIZED:
+                return self._single_result(obs)
+            k = self._hcur
+            self._hcur = 1 - k
+            h_obs, h_rew, h_te, h_tr = self._h_obs[k], self._h_reward[k], self._h_term[k], self._h_trunc[k]
+            h_obs.copy_(obs, non_blocking=True)
+            h_rew.copy_(self._reward, non_blocking=True)
+            h_te.copy_(self._terminated, non_blocking=True)
+            h_tr.copy_(self._truncated, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            o = h_obs.numpy().reshape(self._E, self._D, self._obs_dim)
+            rew, term, trunc = h_rew.numpy(), h_te.numpy(), h_tr.numpy()
+            if self._host_copy:
+                o, rew, term, trunc = o.copy(), rew.copy(), term.copy(), trunc.copy()
+            info = {}
+            if self._final_obs is not None:
+                done = term | trunc
+                info = {"_final_obs": done}
+                if done.any():      # rare: second, blocking D2H of the terminal observations
+                    self._h_final.copy_(self._final_obs)
+                    info["final_obs"] = self._h_final.numpy().reshape(self._E, self._D, self._obs_dim).copy()
+            return o, rew, term, trunc, info
+
+    def _single_result(self, obs):
+        o = self._obs_to_host_single(obs)
+        return (o, float(self._reward[0].item()), bool(self._terminated[0].item()), bool(self._truncated[0].item()),
+                self._computeInfo())
+
+    ################################################################################
+
+    def render(self, mode='human', close=False):
+        """Text printout of the first aviary (BaseAviary.py:387-412); there is no renderer."""
+        st = self._getDroneStateVectors()[0]
+        sc = int(self._step_counter[0].item())
+        print("\n[INFO] BaseAviary.render() ——— it {:04d}".format(sc), "——— simulation time {:.1f}s".format(sc * self.PYB_TIMESTEP))
+        for i in range(self.NUM_DRONES):
+            s = st[i]
+            print("[INFO] BaseAviary.render() ——— drone {:d}".format(i),
+                  "——— x {:+06.2f}, y {:+06.2f}, z {:+06.2f}".format(s[0], s[1], s[2]),
+                  "——— velocity {:+06.2f}, {:+06.2f}, {:+06.2f}".format(s[10], s[11], s[12]),
+                  "——— roll {:+06.2f}, pitch {:+06.2f}, yaw {:+06.2f}".format(s[7] * self.RAD2DEG, s[8] * self.RAD2DEG, s[9] * self.RAD2DEG),
+                  "——— angular velocity {:+06.4f}, {:+06.4f}, {:+06.4f} ——— ".format(s[13], s[14], s[15]))
+
+    def close(self):
+        """Nothing to disconnect (BaseAviary.py:416-421)."""
+
+    def getPyBulletClient(self):
+        """There is no PyBullet client; kept for API compatibility (BaseAviary.py:425-433)."""
+        return -1
+
+    def getDroneIds(self):
+        return np.arange(self.NUM_DRONES)
+
+    ################################################################################
+
+    def _getDroneStateVectors(self):
+        """[E, D, 20] float64 ndarray of _getDroneStateVector (BaseAviary.py:541-561), computed from the state planes."""
+        pos, quat, vel = (self._planes[0, :, 0:3].double(), self._planes[1].double(), self._planes[2, :, 0:3].double())
+        x, y, z, w = quat[:, 0], quat[:, 1], quat[:, 2], quat[:, 3]
+        sarg = -2.0 * (x * z - w * y)
+        roll = torch.atan2(2.0 * (y * z + w * x), w * w - x * x - y * y + z * z)
+        pitch = torch.asin(sarg.clamp(-1, 1))
+        yaw = torch.atan2(2.0 * (x * y + w * z), w * w + x * x - y * y - z * z)
+        rpy = torch.stack([roll, pitch, yaw], dim=1)
+        obs = self._obs_buf[self._cur]
+        ang_v = obs[:, 13:16].double() if self._obs_dim == 20 else obs[:, 9:12].double()
+        sv = torch.cat([pos, quat, rpy, vel, ang_v, self._last_rpm.double()], dim=1)
+        return sv.view(self._E, self._D, 20).cpu().numpy()
+
+    def _getDroneStateVector(self, nth_drone):
+        return self._getDroneStateVectors()[0, nth_drone]
+
+    def _getAdjacencyMatrix(self):
+        """BaseAviary._getAdjacencyMatrix (BaseAviary.py:658-675) for the first aviary."""
+        p = self._planes[0, :self._D, 0:3].double()
+        d = torch.cdist(p, p)
+        return (d < self.NEIGHBOURHOOD_RADIUS).double().cpu().numpy()
+
+    ################################################################################
+    # hooks (BaseAviary.py:1021-1104)
+
+    def _actionSpace(self):
+        raise NotImplementedError
+
+    def _observationSpace(self):
+        raise NotImplementedError
+
+    def _computeInfo(self):
+        return {"answer": 42}
+
+
+_ = spaces

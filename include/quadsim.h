@@ -1,0 +1,184 @@
+/*
+ * quadsim.h -- C ABI of the B200-native vectorised quadrotor simulator (libquadsim.so).
+ *
+ * The reference (utiasDSL/gym-pybullet-drones) is pure Python and has no FFI; this ABI is the
+ * drop-in boundary for its Physics.DYN hot path.  Each entry point names the reference
+ * interface it replaces (paths relative to gym_pybullet_drones/ in the reference tree):
+ *
+ *   qs_step          <- BaseAviary.step (envs/BaseAviary.py:259-383) for BaseRLAviary envs:
+ *                       _preprocessAction (envs/BaseRLAviary.py:160-239), S x _dynamics
+ *                       (envs/BaseAviary.py:815-892), _computeObs KIN (envs/BaseRLAviary.py:307-319),
+ *                       Hover/MultiHover reward/terminated/truncated (envs/HoverAviary.py:68-117,
+ *                       envs/MultiHoverAviary.py:75-130)
+ *   qs_dyn_substeps  <- CtrlAviary step: clip (envs/CtrlAviary.py:121-140) + S x _dynamics +
+ *                       _getDroneStateVector (envs/BaseAviary.py:541-561)
+ *   qs_pid_control   <- DSLPIDControl.computeControl (control/DSLPIDControl.py:82-259) and
+ *                       BaseControl.computeControlFromState (control/BaseControl.py:55-93)
+ *   qs_downwash      <- BaseAviary._downwash (envs/BaseAviary.py:785-811), pairwise term
+ *   qs_reset         <- BaseAviary.reset/_housekeeping (envs/BaseAviary.py:220-255,451-505)
+ *
+ * Conventions
+ *   - plain C, no CUDA/torch types: device buffers are raw pointers owned by the caller; the
+ *     library allocates nothing persistent and keeps no global state but a thread-local error
+ *     string.  "planes" pointers must be 16-byte aligned.
+ *   - every call is asynchronous: it enqueues on `stream` (a cudaStream_t passed as void*) and
+ *     returns; safe under CUDA-graph capture.
+ *   - return value: 0 = ok; <0 = argument error (QS_ERR_*); >0 = cudaError_t of the launch.
+ *     qs_last_error() gives a message for the last non-zero return on the calling thread.
+ *   - arithmetic: state is stored as float32 in HBM and advanced in float64 registers
+ *     (dtype "f64" compute / "f32" storage); see DESIGN.md.
+ */
+#ifndef QUADSIM_H_
+#define QUADSIM_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QS_ABI_VERSION 1
+
+/* drone models (utils/enums.py:3-9) */
+enum { QS_MODEL_CF2X = 0, QS_MODEL_CF2P = 1, QS_MODEL_RACE = 2 };
+
+/* action types (utils/enums.py:33-39); QS_ACT_RAW_RPM is CtrlAviary's clipped raw RPM */
+enum { QS_ACT_RPM = 0, QS_ACT_PID = 1, QS_ACT_VEL = 2, QS_ACT_ONE_D_RPM = 3, QS_ACT_ONE_D_PID = 4, QS_ACT_RAW_RPM = 5 };
+
+/* task (reward / termination rule) */
+enum { QS_TASK_NONE = 0,        /* CtrlAviary: reward -1, never done (envs/CtrlAviary.py:144-200) */
+       QS_TASK_HOVER = 1 };     /* Hover/MultiHover: sum_d max(0, 2-|e_d|^4), sum_d |e_d| < 1e-4, bounds/tilt/time-out */
+
+/* DYN+ aerodynamic terms: the reference's PYB_* force models restated as explicit forces */
+enum { QS_EFFECT_GND = 1, QS_EFFECT_DRAG = 2, QS_EFFECT_DW = 4 };
+
+/* qs_step flags */
+enum { QS_FLAG_AUTORESET_SAME_STEP = 1,   /* SB3 VecEnv semantics: done envs are reset inside the step; the
+                                             terminal observation goes to QsStepIO.final_obs */
+       QS_FLAG_AUTORESET_NEXT_STEP = 2,   /* gymnasium>=1.0 default: a done env is reset by the NEXT step call,
+                                             which ignores that env's action */
+       QS_FLAG_RPY_F32 = 4,               /* evaluate the output roll/pitch/yaw with float32 atan2/asin */
+       /* The reference's reset() clears neither the embedded PID controllers nor the action buffer
+          (SURVEY.md 3.3); autoreset keeps that behaviour unless asked otherwise: */
+       QS_FLAG_AUTORESET_CLEARS_PID = 8,
+       QS_FLAG_AUTORESET_CLEARS_HISTORY = 16,
+       /* Split-substep protocol for aviaries larger than one CTA with downwash (positions couple the drones
+          every substep, so each substep is its own launch: qs_downwash, then qs_step(substeps=1)):
+          all but the last launch of a tick pass SKIP_EPILOGUE (no obs/reward/flags/counter); all but the first
+          pass RPM_FROM_LAST (the rpm decoded by the first launch is re-read from QsState.last_rpm). */
+       QS_FLAG_SKIP_EPILOGUE = 0x100,
+       QS_FLAG_RPM_FROM_LAST = 0x200 };
+
+enum { QS_ERR_NULL = -1, QS_ERR_ALIGN = -2, QS_ERR_SIZE = -3, QS_ERR_ENUM = -4, QS_ERR_UNSUPPORTED = -5 };
+
+/* Physical + task constants.  All double: filled by the host exactly as BaseAviary.__init__ does
+ * (envs/BaseAviary.py:74-128) and passed by value into the launch (kernel constant bank). */
+typedef struct QsParams {
+    double dt;             /* PYB_TIMESTEP = 1/pyb_freq                      BaseAviary.py:83 */
+    double ctrl_dt;        /* CTRL_TIMESTEP = 1/ctrl_freq                    BaseAviary.py:82 */
+    double pyb_freq;       /* PYB_FREQ (for the time-out test)               HoverAviary.py:113 */
+    double m;              /* M                                              cf2x.urdf:11 */
+    double gravity;        /* GRAVITY = G*M                                  BaseAviary.py:117 */
+    double kf, km;         /* KF, KM                                         cf2x.urdf:5 */
+    double j[3];           /* diag(J)                                        cf2x.urdf:12 */
+    double j_inv[3];       /* diag(J^-1)                                     BaseAviary.py:1000 */
+    double hover_rpm;      /* HOVER_RPM                                      BaseAviary.py:118 */
+    double max_rpm;        /* MAX_RPM                                        BaseAviary.py:119 */
+    /* torque mixing of _dynamics (BaseAviary.py:842-854): tau_x = kx * sum_i sx[i] f_i etc.; sz carries RACE's sign flip */
+    double sx[4], sy[4], sz[4];
+    double kx, ky;
+    /* ground effect (BaseAviary.py:715-750) */
+    double gnd_eff_coeff, prop_radius, gnd_eff_h_clip;
+    double prop_xyz[4][3]; /* propeller link COM offsets                      cf2x.urdf:42,54,66,78 */
+    /* drag (BaseAviary.py:754-781), downwash (BaseAviary.py:785-811) */
+    double drag_coeff[3];
+    double dw_coeff[3];
+    /* task constants (HoverAviary.py:51-52,109-115; MultiHoverAviary.py:123-129) */
+    double episode_len_sec, xy_bound, z_bound, tilt_bound, term_dist;
+    /* BaseRLAviary VEL action (BaseRLAviary.py:95) */
+    double speed_limit;
+    /* DSLPIDControl gains/constants (control/DSLPIDControl.py:37-60); pid_gravity/pid_kf are the CONTROLLER's
+     * model constants (BaseControl.py:35-40; BaseRLAviary always embeds CF2X, BaseRLAviary.py:76) */
+    double pid_p_for[3], pid_i_for[3], pid_d_for[3];
+    double pid_p_tor[3], pid_i_tor[3], pid_d_tor[3];
+    double pid_mixer[4][3];
+    double pid_pwm2rpm_scale, pid_pwm2rpm_const, pid_min_pwm, pid_max_pwm;
+    double pid_gravity, pid_kf;
+    int drone_model;       /* QS_MODEL_* (informational; mixing is in sx/sy/sz/kx/ky) */
+    int pad_;
+} QsParams;
+
+/* Per-drone persistent state, structure of arrays, N = n_envs * drones_per_env drones.
+ * planes: float[4][N][4], 16-byte aligned:
+ *   plane 0 = {pos.x, pos.y, pos.z, w.x}   plane 1 = {q.x, q.y, q.z, q.w}  (Bullet order x,y,z,w)
+ *   plane 2 = {vel.x, vel.y, vel.z, w.y}   plane 3 = {w.z, w_lo.x, w_lo.y, w_lo.z}
+ * w = body rates (`rpy_rates`, BaseAviary.py:877).  w_lo = float32 residual of w (w = w_hi + w_lo, ~48-bit
+ * storage in the three otherwise unused lanes: rounding of the body rates is what dominates attitude drift
+ * against the float64 reference).  0 is always a valid value for w_lo. */
+typedef struct QsState {
+    float* planes;                  /* [4][N][4] */
+    float* last_rpm;                /* [N][4] last_clipped_action (BaseAviary.py:372); nullable unless DRAG / RAW_RPM */
+    int* step_counter;              /* [E] physics steps since reset (BaseAviary.py:382) */
+    unsigned char* pending_reset;   /* [E] NEXT_STEP autoreset latch; nullable otherwise */
+    float* pid;                     /* [9][N]: integral_pos_e xyz, last_rpy xyz, integral_rpy_e xyz
+                                       (DSLPIDControl.py:73-78); nullable unless a PID action type */
+    const float* init_pos;          /* [D or N][4] INIT_XYZS (xyz, pad)             BaseAviary.py:194-201 */
+    const float* init_quat;         /* [D or N][4] getQuaternionFromEuler(INIT_RPYS) BaseAviary.py:488 */
+    const float* target_pos;        /* [D or N][4] TARGET_POS (HoverAviary.py:51, MultiHoverAviary.py:71); nullable for QS_TASK_NONE */
+    int tables_per_env;             /* 0: the three tables have D rows shared by all envs; 1: N rows */
+    int pad_;
+} QsState;
+
+/* Inputs/outputs of one control tick. */
+typedef struct QsStepIO {
+    const float* action;        /* [N][A] float32; A = 4 (RPM, VEL, RAW_RPM), 3 (PID), 1 (ONE_D_*) */
+    const float* obs_prev;      /* [N][12+B*A] previous observation: source of the action history (BaseRLAviary.py:316-319) */
+    float* obs;                 /* out: RL: [N][12+B*A] = pos3 rpy3 vel3 ang_v3 + B buffered actions oldest->newest
+                                        RAW_RPM: [N][20] _getDroneStateVector; nullable (state-only step) */
+    float* reward;              /* out [E] */
+    unsigned char* terminated;  /* out [E] */
+    unsigned char* truncated;   /* out [E] */
+    float* final_obs;           /* out [N][obs_dim] rows of envs that finished, SAME_STEP autoreset only; nullable */
+    const float* dw_fz;         /* [N] downwash force along body z from qs_downwash; required iff QS_EFFECT_DW */
+    int act_buffer_size;        /* B = ctrl_freq//2 (BaseRLAviary.py:66); 0 for RAW_RPM */
+    int tick_substeps;          /* physics steps the step counter advances by in the epilogue; 0 = `substeps`
+                                   (only the split-substep protocol passes PYB_STEPS_PER_CTRL here) */
+} QsStepIO;
+
+int qs_abi_version(void);
+const char* qs_last_error(void);
+int qs_sizeof_params(void);
+int qs_sizeof_state(void);
+int qs_sizeof_step_io(void);
+
+/* One control tick for n_envs aviaries of drones_per_env drones: action decode -> `substeps` x DYN ->
+ * obs / reward / terminated / truncated (+ autoreset).  RL action types; task = QS_TASK_HOVER or NONE. */
+int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_type, int task,
+            int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream);
+
+/* CtrlAviary semantics: rpm[N][4] clipped to [0, MAX_RPM], `substeps` x DYN, optional [N][20] state vectors. */
+int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, float* state20_out, const float* dw_fz,
+                    int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream);
+
+/* DSLPIDControl.computeControl for n drones.  cur_pos/cur_quat/cur_vel are read with a row stride (in floats),
+ * so they can point into [n][20] state vectors (strides 20; BaseControl.computeControlFromState) or packed arrays.
+ * target_rpy/target_vel/target_rpy_rates may be NULL (= zeros, the reference defaults).  pid_state: float[9][n]. */
+int qs_pid_control(const QsParams* p, float* pid_state, double control_timestep,
+                   const float* cur_pos, int pos_stride, const float* cur_quat, int quat_stride,
+                   const float* cur_vel, int vel_stride,
+                   const float* target_pos, const float* target_rpy, const float* target_vel, const float* target_rpy_rates,
+                   int n, float* rpm_out, float* pos_e_out, float* yaw_e_out, void* stream);
+
+/* Pairwise downwash within each aviary: fz_out[n] = sum over drones i of the same aviary with dz>0, dxy<10 of
+ * -alpha*exp(-.5 (dxy/beta)^2) (force along n's body z).  Reads positions from the state planes. */
+int qs_downwash(const QsParams* p, const QsState* st, int n_envs, int drones_per_env, float* fz_out, void* stream);
+
+/* Reset envs to their initial pose.  mask: [E] bytes, nullable = all envs.  Zeroes velocities, body rates,
+ * last_rpm, step counter; with reset_pid != 0 also the PID state (the reference never does).
+ * If obs != NULL also refreshes the kinematic part of the RL observation rows (obs_dim > 0) or the [N][20]
+ * state vectors (obs_dim == 20 and act_buffer_size == 0). */
+int qs_reset(const QsParams* p, const QsState* st, const unsigned char* mask, int n_envs, int drones_per_env,
+             int reset_pid, float* obs, int obs_dim, int raw_state20, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUADSIM_H_ */
