@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- drone-steps/s of the fused Physics.DYN control tick on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, weak scaling)
+
+Workload (config.workload): BASELINE configs[2] -- MultiHoverAviary, 65536 drones per GPU as 32768 two-drone
+aviaries, act=RPM (A=4), action buffer B=15 (obs 72 floats), 240 Hz physics / 30 Hz control (S=8 substeps per
+step), random actions in [-1,1], SAME_STEP autoreset (an RL rollout).  One "step" = one env.step() = one launch of
+the fused kernel over all 65536 drones of the rank.  The working set of one batch (42 MB) fits the 126 MB L2, so the
+timed loop rotates over R independent batches (R x 42 MB > L2): every launch finds its inputs in HBM.
+
+JSON keys follow the driver contract; `value` = device-resident steps (actions already in HBM), `e2e` = the same
+steps through the NumPy API (pinned H2D of the actions + D2H of obs/reward/flags inside the timed region),
+`roofline` = algorithmic bytes of the step kernel / its mean launch duration (CUDA events around each launch)
+against MEASURED_PEAKS.json, `cpu_baseline` = the float64 NumPy oracle on a bounded sample on this host.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DRONES_PER_GPU = 65536
+D = 2                    # drones per aviary (learn.py DEFAULT_AGENTS)
+A, B, S = 4, 15, 8       # action width, action-buffer length, substeps per control tick
+OBS_DIM = 12 + A * B
+# ALGORITHMIC bytes per drone-step (SURVEY.md 8d, W-RL(A=4,B=15)): state 52 r + 52 w, action 16 r, history 4*A*(B-1) r,
+# obs 4*(12+B*A) w, per-aviary counter/reward/flags (4 r + 4+4+2 w) counted per drone as in the survey = 646 B
+ALG_BYTES = 52 + 52 + 4 * A + 4 * A * (B - 1) + 4 + 4 * OBS_DIM + 4 + 2 + 4
+METRIC = "drone-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batches", type=int, default=8, help="independent 65536-drone batches rotated through (L2 defeat)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU legs: the float64 NumPy oracle (port of the reference's DYN path), never the product
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_worker(args):
+    n_envs, steps, seed = args
+    import numpy as np
+    from oracle.dyn_oracle import OracleAviary
+    env = OracleAviary("multihover", n_envs, D, act="rpm")
+    env.reset()
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(-1, 1, (steps, n_envs, D, A)).astype(np.float32)
+    t0 = time.perf_counter()
+    for t in range(steps):
+        obs, rew, term, trunc = env.step(acts[t])
+        done = term | trunc
+        if done.any():
+            env.reset(mask=done)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_single(n_envs=2048, steps=1000):
+    """Bounded sample on one core: 4096 drones x `steps` control ticks of the same workload."""
+    dt = _oracle_worker((n_envs, steps, 0))
+    return {"value": n_envs * D * steps / dt, "unit": METRIC, "cores": 1, "kind": "port",
+            "sample": "%d drones x %d steps (S=%d) of the bench workload, float64 NumPy oracle, %.1f s" % (n_envs * D, steps, S, dt)}
+
+
+def reference_arm(a):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot travel
+    to the GPU box, so this is the oracle port (batched float64 NumPy restatement pinned to the reference by
+    tests/golden), fanned out over every host core; each step is a bounded sample of the workload."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_proc_envs = 2048                      # 4096 drones per process per step
+    steps, warm = max(1, min(a.steps, 500)), max(1, min(a.warmup, 5))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_oracle_worker, [(per_proc_envs, warm, 100 + i) for i in range(cores)])
+        t0 = time.perf_counter()
+        pool.map(_oracle_worker, [(per_proc_envs, steps, i) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    drones = per_proc_envs * D * cores
+    val = drones * steps / wall
+    sample = "%d processes x %d drones x %d steps (S=%d), float64 NumPy oracle port" % (cores, per_proc_envs * D, steps, S)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": METRIC, "n_gpus": a.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, drones),
+        "cpu_baseline": {"value": val, "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(a, drones_per_step):
+    return {"workload": "MultiHoverAviary x %d aviaries x %d drones (=%d drones per GPU), act=RPM (A=4), action buffer B=15, obs 72 f32, "
+                        "pyb 240 Hz / ctrl 30 Hz (S=8), random actions, SAME_STEP autoreset [BASELINE configs[2]]" % (DRONES_PER_GPU // D, D, DRONES_PER_GPU),
+            "drones_per_gpu": DRONES_PER_GPU, "drones_per_step": drones_per_step, "substeps_per_step": S, "obs_dim": OBS_DIM,
+            "parallelism": "env-sharded x%d (no collective on the step path)" % a.gpus,
+            "l2": "%d rotating independent batches x 42 MB > 126 MB L2 (no flush kernel in the timed region)" % a.batches}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gym_pybullet_drones_b200.envs import MultiHoverAviary
+    from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
+
+    E = DRONES_PER_GPU // D
+    R = a.batches
+    envs = [MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E, device=dev,
+                             autoreset="same_step", host_copy=False) for _ in range(R)]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    acts = [torch.rand((E, D, A), device=dev, generator=gen) * 2 - 1 for _ in range(R)]
+    for e in envs:
+        e.reset()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n, k0=0):
+        for k in range(n):
+            i = (k0 + k) % R
+            envs[i].step(acts[i])
+
+    # ---- device-resident throughput --------------------------------------------------------------------------
+    run(a.warmup)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        run(a.steps, a.warmup)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        # keep the sampler over a little more load so short runs still see clocks under load
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            run(50)
+        torch.cuda.synchronize()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = DRONES_PER_GPU * world * a.steps / (ms_max * 1e-3)
+
+    # ---- per-launch kernel time for the roofline (events around every launch, L2-cold thanks to the rotation) ---
+    kt = []
+    n_k = min(a.steps, 400)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k)]
+    torch.cuda.synchronize()
+    for k in range(n_k):
+        i = k % R
+        evs[k][0].record()
+        envs[i].step(acts[i])
+        evs[k][1].record()
+    torch.cuda.synchronize()
+    kt = [s.elapsed_time(e) for s, e in evs]
+    kern_ms = statistics.mean(kt)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = ALG_BYTES * DRONES_PER_GPU / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": None, "kernel": "step_kernel<0,false>", "kernel_ms": kern_ms, "kernel_ms_median": statistics.median(kt),
+                "alg_bytes_per_drone_step": ALG_BYTES, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)"}
+
+    # ---- end to end through the NumPy API: pinned H2D of actions, D2H of obs/reward/flags in the timed region ----
+    h_acts = [x.cpu().numpy() for x in acts]
+    e2e_steps = max(10, min(a.steps, 200))
+    for k in range(5):
+        envs[k % R].step(h_acts[k % R])
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        i = k % R
+        obs, rew, term, trunc, info = envs[i].step(h_acts[i])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = DRONES_PER_GPU * world * e2e_steps / float(t.item())
+    h2d = DRONES_PER_GPU * A * 4
+    d2h = DRONES_PER_GPU * OBS_DIM * 4 + E * (4 + 1 + 1)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(a, DRONES_PER_GPU * world),
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "MultiHoverAviary.step(ndarray) -> ndarrays (pinned staging, host_copy=False)"},
+            "gpu_launches": a.steps,
+            "roofline": roofline,
+            "substeps_per_s": value * S,
+            "state_storage": "f32 planes (+f32 residual lanes for body rates); arithmetic f64",
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_single()
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

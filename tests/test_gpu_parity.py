@@ -1,0 +1,455 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI via the product env/controller classes,
+against (a) golden vectors of the unmodified reference, (b) the float64 NumPy oracle on seeded inputs at sizes it
+finishes in seconds, (c) size-independent properties at BASELINE.json's full sizes.
+
+Tolerance (north star): |a - b| <= 1e-5 * max(|b|, 1) element-wise on the kinematic state over 1000 physics steps
+(RTOL).  Quaternions are compared up to sign."""
+import numpy as np
+import pytest
+import torch
+
+from qs_testlib import FIELDS, RTOL, quat_err, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _imports():
+    from gym_pybullet_drones_b200.control import DSLPIDControl
+    from gym_pybullet_drones_b200.envs import CtrlAviary, HoverAviary, MultiHoverAviary
+    from gym_pybullet_drones_b200.utils.enums import ActionType, DroneModel, Physics
+    from oracle import dyn_oracle as O
+    return DSLPIDControl, CtrlAviary, HoverAviary, MultiHoverAviary, ActionType, DroneModel, Physics, O
+
+
+def state_of(env):
+    """float64 host copies of the kinematic state [E,D,.] + the derived rpy/ang_v of the last observation."""
+    obs = env._obs_buf[env._cur].view(env._E, env._D, env._obs_dim).double().cpu().numpy()
+    out = dict(pos=env.pos.double().cpu().numpy(), quat=env.quat.double().cpu().numpy(), vel=env.vel.double().cpu().numpy(),
+               rpy_rates=env.rpy_rates.cpu().numpy())
+    if env._obs_dim == 20:
+        out["rpy"], out["ang_v"] = obs[..., 7:10], obs[..., 13:16]
+    else:
+        out["rpy"], out["ang_v"] = obs[..., 3:6], obs[..., 9:12]
+    return out
+
+
+def check_fields(st, g, key, t, tol=RTOL, env_idx=0):
+    for f in FIELDS:
+        ref = g[key + "_" + f][t]
+        mine = st[f][env_idx]
+        e = quat_err(mine, ref) if f == "quat" else relerr(mine, ref)
+        assert e <= tol, (key, f, t, e)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (a) golden vectors of the reference
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cf,steps", [(240, 1000), (30, 125)])
+@pytest.mark.parametrize("stream", ["zeros", "rand", "sine", "const"])
+def test_config1_hover_1000_physics_steps(golden, cf, steps, stream):
+    """BASELINE config 1 on the GPU: every element of pos/quat/rpy/vel/ang_v/rpy_rates within 1e-5 rel for 1000 physics
+    steps; E=3 identical aviaries also checks that lanes do not interact."""
+    _, _, HoverAviary, _, ActionType, _, Physics, _ = _imports()
+    g = golden("hover_rpm_1000")
+    key = "cf%d_%s" % (cf, stream)
+    env = HoverAviary(physics=Physics.DYN, pyb_freq=240, ctrl_freq=cf, act=ActionType.RPM, num_envs=3)
+    obs, _ = env.reset()
+    assert relerr(obs[0].cpu().numpy(), g[key + "_obs0"]) < 1e-6
+    acts = g[key + "_actions"]
+    tol = RTOL if stream != "const" else 1e-4
+    for t in range(min(steps, acts.shape[0])):
+        a = torch.from_numpy(np.broadcast_to(acts[t], (3, 1, 4)).copy()).cuda()
+        obs, rew, term, trunc, _ = env.step(a)
+        st = state_of(env)
+        check_fields(st, g, key, t, tol, 0)
+        check_fields(st, g, key, t, tol, 2)
+        assert abs(float(rew[0]) - g[key + "_reward"][t]) < 1e-5
+        assert bool(term[0]) == bool(g[key + "_terminated"][t]) and bool(trunc[0]) == bool(g[key + "_truncated"][t]), t
+        if t % 50 == 0:
+            assert relerr(obs[0].cpu().numpy(), g[key + "_obs"][t // 50]) < tol
+
+
+def test_learn_config_episode_single_env_api(golden):
+    """learn.py's config through the reference's single-env API: time-out on env step 242, return 333.8626."""
+    _, _, HoverAviary, _, ActionType, _, Physics, _ = _imports()
+    g = golden("hover_one_d_rpm_episode")
+    env = HoverAviary(physics=Physics.DYN, act=ActionType.ONE_D_RPM)
+    obs, info = env.reset(seed=42, options={})
+    assert isinstance(obs, np.ndarray) and obs.shape == (1, 27) and obs.dtype == np.float32 and info == {"answer": 42}
+    assert env.action_space.shape == (1, 1) and env.observation_space.shape == (1, 27)
+    ret, n = 0.0, 0
+    for t in range(250):
+        obs, r, te, tr, info = env.step(np.zeros((1, 1), np.float32))
+        assert isinstance(r, float) and isinstance(te, bool) and isinstance(tr, bool)
+        assert abs(r - g["reward"][t]) < 1e-5 and tr == bool(g["truncated"][t])
+        if n == 0:
+            ret += r
+            if te or tr:
+                n = t + 1
+    assert n == 242 and abs(ret - 333.862626904298) < 1e-2
+    assert env.step_counter == 250 * 8 and env.CTRL_FREQ == 30 and env.EPISODE_LEN_SEC == 8
+
+
+@pytest.mark.parametrize("key,nd,act", [("d2_one_d_rpm", 2, "ONE_D_RPM"), ("d2_rpm", 2, "RPM"), ("d3_rpm", 3, "RPM")])
+def test_multihover_golden(golden, key, nd, act):
+    _, _, _, MultiHoverAviary, ActionType, _, Physics, _ = _imports()
+    g = golden("multihover_rand_300")
+    env = MultiHoverAviary(num_drones=nd, physics=Physics.DYN, act=ActionType[act], num_envs=2)
+    assert relerr(env.TARGET_POS, g[key + "_TARGET_POS"]) == 0
+    obs, _ = env.reset()
+    acts = g[key + "_actions"]
+    for t in range(125):      # 1000 physics steps
+        a = torch.from_numpy(np.broadcast_to(acts[t], (2,) + acts[t].shape).copy()).cuda()
+        obs, rew, term, trunc, _ = env.step(a)
+        check_fields(state_of(env), g, key, t, RTOL, 1)
+        assert abs(float(rew[1]) - g[key + "_reward"][t]) < 2e-5 * max(1.0, abs(g[key + "_reward"][t]))
+        assert bool(term[1]) == bool(g[key + "_terminated"][t]) and bool(trunc[1]) == bool(g[key + "_truncated"][t]), t
+        if t % 10 == 0:
+            assert relerr(obs[1].cpu().numpy(), g[key + "_obs"][t // 10]) < RTOL
+
+
+@pytest.mark.parametrize("model", ["CF2P", "RACE"])
+def test_ctrl_aviary_other_models(golden, model):
+    _, CtrlAviary, _, _, _, DroneModel, Physics, _ = _imports()
+    g = golden("ctrl_models_300")
+    dm = DroneModel[model]
+    key = dm.value
+    env = CtrlAviary(drone_model=dm, num_drones=2, physics=Physics.DYN, pyb_freq=240, ctrl_freq=120)
+    obs, _ = env.reset()
+    assert obs.shape == (2, 20) and relerr(obs, g[key + "_obs0"]) < 1e-6
+    acts = g[key + "_actions"]
+    for t in range(acts.shape[0]):
+        obs, r, te, tr, _ = env.step(acts[t])
+        ref = g[key + "_obs"][t]
+        assert r == -1 and te is False and tr is False
+        assert relerr(obs[:, 0:3], ref[:, 0:3]) < 3e-5 and quat_err(obs[:, 3:7], ref[:, 3:7]) < 3e-5, t
+        assert relerr(obs[:, 7:16], ref[:, 7:16]) < 1e-4 and relerr(obs[:, 16:20], ref[:, 16:20]) < 1e-7, t
+
+
+@pytest.mark.parametrize("model", ["CF2X", "CF2P"])
+def test_pid_known_answers(golden, model):
+    """DSLPIDControl.computeControl on 256 random states x 3 stateful calls (float32 inputs: 1e-5 on rpm)."""
+    DSLPIDControl, _, _, _, _, DroneModel, _, _ = _imports()
+    g = golden("pid_kat")
+    dm = DroneModel[model]
+    k = dm.value + "_"
+    n = g[k + "pos"].shape[0]
+    ctrl = DSLPIDControl(dm, num_drones=n)
+    for call in range(3):
+        rpm, pe, ye = ctrl.computeControl(1 / 48, g[k + "pos"] + 0.01 * call, g[k + "quat"], g[k + "vel"], None, g[k + "target_pos"],
+                                          g[k + "target_rpy"], g[k + "target_vel"], g[k + "target_rpy_rates"])
+        assert relerr(rpm, g[k + "rpm"][call]) < 2e-5, call
+        assert relerr(pe, g[k + "pos_e"][call]) < 1e-6 and relerr(ye, g[k + "yaw_e"][call]) < 1e-6
+        assert relerr(ctrl.integral_pos_e, g[k + "integral_pos_e"][call]) < 1e-6
+        assert relerr(ctrl.last_rpy, g[k + "last_rpy"][call]) < 1e-6
+        assert relerr(ctrl.integral_rpy_e, g[k + "integral_rpy_e"][call]) < 1e-5
+    one = DSLPIDControl(dm)
+    r1, p1, y1 = one.computeControl(1 / 48, g[k + "pos"][0], g[k + "quat"][0], g[k + "vel"][0], np.zeros(3), g[k + "target_pos"][0])
+    assert r1.shape == (4,) and p1.shape == (3,) and isinstance(y1, float)
+
+
+PID_CASES = [("hover_d1_pid", 1, "PID"), ("hover_d1_vel", 1, "VEL"), ("hover_d1_one_d_pid", 1, "ONE_D_PID"), ("multi_d2_pid", 2, "PID")]
+
+
+def _pid_env(nd, act, cf):
+    _, _, HoverAviary, MultiHoverAviary, ActionType, _, Physics, _ = _imports()
+    kw = dict(physics=Physics.DYN, act=ActionType[act], pyb_freq=240, ctrl_freq=cf, num_envs=1)
+    return HoverAviary(**kw) if nd == 1 else MultiHoverAviary(num_drones=nd, **kw)
+
+
+@pytest.mark.parametrize("key,nd,act", PID_CASES)
+def test_rl_pid_teacher_forced_30hz(golden, key, nd, act):
+    g = golden("rl_pid_cf30")
+    env = _pid_env(nd, act, 30)
+    env.reset()
+    acts = g[key + "_actions"]
+    for t in range(acts.shape[0]):
+        if t > 0:
+            env.set_state(pos=g[key + "_pos"][t - 1], quat=g[key + "_quat"][t - 1], vel=g[key + "_vel"][t - 1],
+                          rpy_rates=g[key + "_rpy_rates"][t - 1], step_counter=t * 8)
+            env._pid[0:3] = torch.from_numpy(g[key + "_pid_integral_pos_e"][t - 1].T.astype(np.float32)).cuda()
+            env._pid[3:6] = torch.from_numpy(g[key + "_pid_last_rpy"][t - 1].T.astype(np.float32)).cuda()
+            env._pid[6:9] = torch.from_numpy(g[key + "_pid_integral_rpy_e"][t - 1].T.astype(np.float32)).cuda()
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(acts[t][None]).cuda())
+        check_fields(state_of(env), g, key, t, 2e-5)
+        assert abs(float(rew[0]) - g[key + "_reward"][t]) < 1e-4 and bool(trunc[0]) == bool(g[key + "_truncated"][t])
+
+
+@pytest.mark.parametrize("key,nd,act", PID_CASES)
+def test_rl_pid_trajectory_120hz(golden, key, nd, act):
+    g = golden("rl_pid_cf120")
+    env = _pid_env(nd, act, 120)
+    env.reset()
+    acts = g[key + "_actions"]
+    for t in range(acts.shape[0]):
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(acts[t][None]).cuda())
+        check_fields(state_of(env), g, key, t, 5e-5)
+        if t % 10 == 0:
+            assert relerr(obs[0].cpu().numpy(), g[key + "_obs"][t // 10]) < 5e-5
+
+
+def test_pid_circle_workload(golden):
+    """examples/pid.py: CtrlAviary(DYN, 240/48) x 3 + DSLPIDControl through computeControlFromState; free-running for 30
+    ticks, then teacher-forced (the 48 Hz loop amplifies rounding ~1.5x per tick in the reference itself)."""
+    DSLPIDControl, CtrlAviary, _, _, _, DroneModel, Physics, _ = _imports()
+    g = golden("pid_circle_cf2x")
+    env = CtrlAviary(num_drones=3, initial_xyzs=g["INIT_XYZS"], initial_rpys=g["INIT_RPYS"], physics=Physics.DYN, pyb_freq=240, ctrl_freq=48)
+    ctrl = DSLPIDControl(DroneModel.CF2X, num_drones=3)
+    env.reset()
+    action = np.zeros((3, 4))
+    for t in range(g["obs"].shape[0]):
+        if t > 30:
+            st = g["obs"][t - 1]
+            env.set_state(pos=st[:, 0:3], quat=st[:, 3:7], vel=st[:, 10:13], rpy_rates=g["rpy_rates"][t - 1])
+            ctrl.set_state(g["pid_integral_pos_e"][t - 1], g["pid_last_rpy"][t - 1], g["pid_integral_rpy_e"][t - 1])
+            action = g["action"][t - 1]
+        obs, _, _, _, _ = env.step(action)
+        ref = g["obs"][t]
+        tol = 5e-5 if t <= 30 else 2e-5
+        assert relerr(obs[:, 0:3], ref[:, 0:3]) < tol and quat_err(obs[:, 3:7], ref[:, 3:7]) < tol and relerr(obs[:, 7:16], ref[:, 7:16]) < 10 * tol, t
+        rpm, pe, ye = ctrl.computeControlFromState(env.CTRL_TIMESTEP, obs, g["target"][t], target_rpy=g["INIT_RPYS"])
+        if t > 30:
+            assert relerr(rpm, g["action"][t]) < 1e-4, t
+        action = rpm
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (b) seeded inputs against the float64 oracle
+# ---------------------------------------------------------------------------------------------------------------
+def _borderline(ora, eps=1e-4):
+    """[E] bool: some truncation test of the oracle state sits within eps of its threshold."""
+    m = np.minimum.reduce([np.abs(np.abs(ora.pos[..., 0]) - ora.xy_bound), np.abs(np.abs(ora.pos[..., 1]) - ora.xy_bound),
+                           np.abs(ora.pos[..., 2] - 2.0), np.abs(np.abs(ora.rpy[..., 0]) - 0.4), np.abs(np.abs(ora.rpy[..., 1]) - 0.4)])
+    return np.any(m < eps, axis=1)
+
+
+def _compare_with_oracle(env, ora, acts, tol, check_obs_every=5):
+    obs, _ = env.reset()
+    o_obs = ora.reset()
+    assert relerr(obs.cpu().numpy(), o_obs) < 1e-6
+    for t in range(acts.shape[0]):
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(acts[t]).cuda())
+        o_obs, o_rew, o_term, o_trunc = ora.step(acts[t])
+        st = state_of(env)
+        for f in FIELDS:
+            ref = getattr(ora, f)
+            e = quat_err(st[f], ref) if f == "quat" else relerr(st[f], ref)
+            assert e <= tol, (f, t, e)
+        assert relerr(rew.cpu().numpy(), o_rew) < 10 * tol
+        assert np.array_equal(term.cpu().numpy(), o_term), t
+        # a truncation bound crossed within rounding distance of the threshold may legitimately flip: skip those envs
+        clear = ~_borderline(ora)
+        assert np.array_equal(trunc.cpu().numpy()[clear], o_trunc[clear]), t
+        if t % check_obs_every == 0:
+            assert relerr(obs.cpu().numpy(), o_obs) < tol
+
+
+@pytest.mark.parametrize("act,A", [("RPM", 4), ("ONE_D_RPM", 1)])
+def test_config3_multihover_4096_vs_oracle(act, A):
+    """MultiHover, E=2048 x D=2 (4096 drones), random actions, 125 ticks x 8 substeps = 1000 physics steps."""
+    _, _, _, MultiHoverAviary, ActionType, _, Physics, O = _imports()
+    E, D, T = 2048, 2, 125
+    rng = np.random.default_rng(123)
+    acts = rng.uniform(-1, 1, (T, E, D, A)).astype(np.float32)
+    env = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType[act], num_envs=E)
+    ora = O.OracleAviary("multihover", E, D, act=act.lower())
+    _compare_with_oracle(env, ora, acts, RTOL)
+
+
+def test_config2_pid_4096_fixed_setpoints_vs_oracle():
+    """BASELINE config 2 shape: 4096 x HoverAviary with the embedded DSLPIDControl (act=PID).  At the RL default 30 Hz the
+    loop is chaotic in the reference itself, so the free-running comparison uses 240/120 Hz (S=2) for 250 ticks."""
+    _, _, HoverAviary, _, ActionType, _, Physics, O = _imports()
+    E, T = 4096, 250
+    g = torch.Generator().manual_seed(0)
+    sp = (torch.tensor([-0.5, -0.5, 0.5]) + torch.rand((E, 1, 3), generator=g) * torch.tensor([1.0, 1.0, 1.0])).numpy().astype(np.float32)
+    acts = np.broadcast_to(sp, (T, E, 1, 3)).copy()
+    env = HoverAviary(physics=Physics.DYN, act=ActionType.PID, pyb_freq=240, ctrl_freq=120, num_envs=E)
+    ora = O.OracleAviary("hover", E, 1, act="pid", ctrl_freq=120)
+    _compare_with_oracle(env, ora, acts, 5e-5, check_obs_every=25)
+
+
+@pytest.mark.parametrize("phys,eff", [("PYB_GND", 1), ("PYB_DRAG", 2), ("PYB_DW", 4), ("PYB_GND_DRAG_DW", 7)])
+def test_dynplus_effects_vs_oracle(phys, eff):
+    """DYN+ terms (ground effect, drag, in-CTA downwash): 64 aviaries x 4 close drones, 60 ticks x 8 substeps."""
+    _, _, _, MultiHoverAviary, ActionType, _, Physics, O = _imports()
+    E, D, T = 64, 4, 60
+    xyz = np.array([[0.0, 0.0, 0.06], [0.05, 0.02, 0.4], [0.1, -0.03, 0.75], [-0.05, 0.05, 1.1]])
+    rng = np.random.default_rng(5)
+    acts = (0.3 * rng.uniform(-1, 1, (T, E, D, 4))).astype(np.float32)
+    env = MultiHoverAviary(num_drones=D, initial_xyzs=xyz, physics=Physics[phys], act=ActionType.RPM, num_envs=E)
+    ora = O.OracleAviary("multihover", E, D, act="rpm", initial_xyzs=xyz, effects=eff)
+    _compare_with_oracle(env, ora, acts, 2e-5)
+
+
+def test_config4_big_formation_downwash_vs_oracle():
+    """Config 4 shape at oracle-sized N: ONE aviary of 1024 drones in a 32x32 grid (0.25 m pitch, four height layers) with
+    ground effect + downwash: the tiled pairwise kernel + split-substep protocol against the O(N^2) NumPy oracle."""
+    _, CtrlAviary, _, _, _, _, Physics, O = _imports()
+    D, T = 1024, 10
+    i = np.arange(D)
+    xyz = np.stack([0.25 * (i % 32), 0.25 * (i // 32), 0.5 + 0.5 * (i % 4)], axis=1)
+    env = CtrlAviary(num_drones=D, initial_xyzs=xyz, physics=Physics.PYB_GND_DRAG_DW, pyb_freq=240, ctrl_freq=48, num_envs=1)
+    ora = O.OracleAviary("ctrl", 1, D, ctrl_freq=48, initial_xyzs=xyz, effects=7)
+    rng = np.random.default_rng(9)
+    env.reset(); ora.reset()
+    # the pair term itself at step 0
+    import ctypes as C
+    from gym_pybullet_drones_b200 import _native as N
+    fz = torch.zeros(D, device="cuda")
+    N.check(N.lib().qs_downwash(C.byref(env._P), C.byref(env._st), 1, D, fz.data_ptr(), torch.cuda.current_stream().cuda_stream), "qs_downwash")
+    ref_fz = O.downwash_body_z(ora.P, ora.pos)[0]
+    assert np.count_nonzero(ref_fz) > 700 and relerr(fz.cpu().numpy(), ref_fz) < 1e-5
+    for t in range(T):
+        a = (ora.P.HOVER_RPM * (1 + 0.05 * rng.uniform(-1, 1, (1, D, 4)))).astype(np.float32)
+        obs, _, _, _, _ = env.step(torch.from_numpy(a).cuda())
+        o_obs, _, _, _ = ora.step(a)
+        o = obs.cpu().numpy()
+        assert relerr(o[..., 0:3], o_obs[..., 0:3]) < 2e-5 and quat_err(o[..., 3:7], o_obs[..., 3:7]) < 2e-5, t
+        assert relerr(o[..., 7:16], o_obs[..., 7:16]) < 1e-4, t
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# autoreset / vector-env semantics
+# ---------------------------------------------------------------------------------------------------------------
+def test_autoreset_same_step_matches_manual_reset_loop():
+    """SB3 VecEnv semantics: done envs return the reset observation, the terminal one lands in info['final_obs'];
+    compared with an oracle loop that resets done envs by hand (the reference's reset keeps the action buffer)."""
+    _, _, HoverAviary, _, ActionType, _, Physics, O = _imports()
+    E, T = 512, 300
+    rng = np.random.default_rng(77)
+    acts = rng.uniform(-1, 1, (T, E, 1, 4)).astype(np.float32)
+    env = HoverAviary(physics=Physics.DYN, act=ActionType.RPM, num_envs=E, autoreset="same_step")
+    ora = O.OracleAviary("hover", E, 1, act="rpm")
+    env.reset(); ora.reset()
+    n_done = 0
+    for t in range(T):
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(acts[t]).cuda())
+        o_obs, o_rew, o_term, o_trunc = ora.step(acts[t])
+        done = o_term | o_trunc
+        assert np.array_equal((term | trunc).cpu().numpy(), done), t
+        assert np.array_equal(info["_final_obs"].cpu().numpy(), done)
+        if done.any():
+            n_done += int(done.sum())
+            assert relerr(info["final_obs"].cpu().numpy()[done], o_obs[done]) < 2e-5
+            o_obs2 = ora.reset(mask=done)
+            o_obs = o_obs2
+        assert relerr(obs.cpu().numpy(), o_obs) < 2e-5, t
+        assert np.array_equal(env.step_counter.cpu().numpy(), ora.step_counter), t
+    assert n_done > E // 2      # random +-5 % RPM tips the drone past 0.4 rad quickly: plenty of resets exercised
+
+
+def test_autoreset_next_step_semantics():
+    _, _, HoverAviary, _, ActionType, _, Physics, O = _imports()
+    E, T = 256, 200
+    rng = np.random.default_rng(78)
+    acts = rng.uniform(-1, 1, (T, E, 1, 4)).astype(np.float32)
+    env = HoverAviary(physics=Physics.DYN, act=ActionType.RPM, num_envs=E, autoreset="next_step")
+    ora = O.OracleAviary("hover", E, 1, act="rpm")
+    env.reset(); ora.reset()
+    pending = np.zeros(E, bool)
+    saw = 0
+    for t in range(T):
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(acts[t]).cuda())
+        # oracle: envs that finished last step are reset now (their action is ignored, the buffer is untouched)
+        buf_before = [b.copy() for b in ora.action_buffer]
+        snap = {f: getattr(ora, f).copy() for f in ("pos", "quat", "vel", "rpy_rates", "ang_v", "rpy", "last_clipped_action")}
+        sc = ora.step_counter.copy()
+        o_obs, o_rew, o_term, o_trunc = ora.step(acts[t])
+        if pending.any():
+            saw += int(pending.sum())
+            for f, v in snap.items():
+                getattr(ora, f)[pending] = v[pending]
+            ora.step_counter[pending] = sc[pending]
+            for b_new, b_old in zip(ora.action_buffer, buf_before):
+                b_new[pending] = b_old[pending]
+            o_obs_r = ora.reset(mask=pending)
+            o_obs[pending] = o_obs_r[pending]
+            o_rew[pending] = 0; o_term[pending] = False; o_trunc[pending] = False
+        assert relerr(obs.cpu().numpy(), o_obs) < 2e-5, t
+        assert relerr(rew.cpu().numpy(), o_rew) < 1e-4
+        assert np.array_equal((term | trunc).cpu().numpy(), o_term | o_trunc), t
+        pending = o_term | o_trunc
+    assert saw > E // 4
+
+
+def test_numpy_vector_api_roundtrip_equals_tensor_api():
+    _, _, _, MultiHoverAviary, ActionType, _, Physics, _ = _imports()
+    E, D = 128, 2
+    rng = np.random.default_rng(3)
+    e1 = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E)
+    e2 = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E)
+    o1, _ = e1.reset(); o2, _ = e2.reset()
+    for t in range(20):
+        a = rng.uniform(-1, 1, (E, D, 4)).astype(np.float32)
+        o1, r1, te1, tr1, _ = e1.step(torch.from_numpy(a).cuda())
+        o2, r2, te2, tr2, _ = e2.step(a)
+        assert isinstance(o2, np.ndarray) and o2.dtype == np.float32 and r2.shape == (E,) and te2.dtype == bool
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(te1.cpu().numpy(), te2) and np.array_equal(tr1.cpu().numpy(), tr2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (c) size-independent properties at BASELINE.json's full sizes
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_65536_properties():
+    """65536 drones (32768 x MultiHover D=2), 100 random ticks: unit quaternions, finite state, every aviary that received
+    the same action stream has bit-identical state (position in the batch does not matter), reset is idempotent."""
+    _, _, _, MultiHoverAviary, ActionType, _, Physics, _ = _imports()
+    E, D, T = 32768, 2, 100
+    env = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E, autoreset="same_step")
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    base = torch.rand((T, 64, D, 4), device="cuda", generator=gen) * 2 - 1
+    for t in range(T):
+        a = base[t].repeat(E // 64, 1, 1)           # aviary e gets stream e % 64
+        obs, rew, term, trunc, _ = env.step(a)
+    torch.cuda.synchronize()
+    q = env.quat.double()
+    assert torch.all(torch.isfinite(env._planes)) and torch.all(torch.isfinite(obs))
+    assert float((q.norm(dim=-1) - 1).abs().max()) < 2e-7
+    pl = env._planes.view(4, E // 64, 64, D, 4)
+    assert torch.equal(pl[:, 0], pl[:, 1]) and torch.equal(pl[:, 0], pl[:, -1])
+    ob = obs.view(E // 64, 64, D, -1)
+    assert torch.equal(ob[0], ob[-1]) and torch.equal(rew.view(-1, 64)[0], rew.view(-1, 64)[-1])
+    o1, _ = env.reset(); p1 = env._planes.clone()
+    o2, _ = env.reset()
+    assert torch.equal(p1, env._planes) and torch.equal(o1[..., :12], o2[..., :12])
+    assert int(env.step_counter.max()) == 0
+
+
+def test_history_shift_is_exact():
+    """The observation tail is the last B actions oldest -> newest, bit-exact (BaseRLAviary.py:316-319)."""
+    _, _, HoverAviary, _, ActionType, _, Physics, _ = _imports()
+    for act, A in (("RPM", 4), ("PID", 3), ("ONE_D_RPM", 1)):
+        E = 333
+        env = HoverAviary(physics=Physics.DYN, act=ActionType[act], num_envs=E)
+        env.reset()
+        rng = np.random.default_rng(1)
+        hist = [np.zeros((E, 1, A), np.float32) for _ in range(15)]
+        for t in range(40):
+            a = rng.uniform(-1, 1, (E, 1, A)).astype(np.float32)
+            if act == "PID":
+                a = (a * 0.1 + np.array([0, 0, 0.5], np.float32)).astype(np.float32)
+            obs, *_ = env.step(a)
+            hist = hist[1:] + [a]
+            assert np.array_equal(obs[..., 12:], np.concatenate(hist, axis=-1)), (act, t)
+
+
+def test_abi_argument_errors():
+    import ctypes as C
+    from gym_pybullet_drones_b200 import _native as N
+    _, _, HoverAviary, _, ActionType, _, Physics, _ = _imports()
+    env = HoverAviary(physics=Physics.DYN, act=ActionType.RPM, num_envs=4)
+    L = N.lib()
+    io = env._io
+    io.action = env._action_dev.data_ptr(); io.obs_prev = env._obs_buf[0].data_ptr(); io.obs = env._obs_buf[1].data_ptr()
+    s = torch.cuda.current_stream().cuda_stream
+    assert L.qs_step(C.byref(env._P), C.byref(env._st), C.byref(io), 99, 1, 4, 1, 8, 0, 0, s) == -4
+    assert L.qs_step(C.byref(env._P), C.byref(env._st), C.byref(io), 0, 1, 0, 1, 8, 0, 0, s) == -3
+    assert L.qs_step(None, C.byref(env._st), C.byref(io), 0, 1, 4, 1, 8, 0, 0, s) == -1
+    io.action = env._action_dev.data_ptr() + 4
+    assert L.qs_step(C.byref(env._P), C.byref(env._st), C.byref(io), 0, 1, 4, 1, 8, 0, 0, s) == -2
+    assert b"aligned" in L.qs_last_error()
+    with pytest.raises(ValueError):
+        N.check(-2, "x")
