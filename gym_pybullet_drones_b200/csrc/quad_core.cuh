@@ -315,6 +315,7 @@ QS_HD void pid_control(const QsParams& P, PidState& st, double dt,
 // ---- action decoding (BaseRLAviary._preprocessAction, envs/BaseRLAviary.py:160-239) -----------------
 // `a` = this drone's float32 action; `der` = the cached kinematics the reference reads through
 // _getDroneStateVector (rpy from the end of the previous tick).  PID variants update `pst`.
+template <bool PIDACT>
 QS_HD void decode_action(const QsParams& P, int act_type, const float a[4], const Drone& d, double cur_yaw,
                          PidState& pst, double rpm[4]) {
     if (act_type == QS_ACT_RPM) {                                                    // :192
@@ -326,7 +327,7 @@ QS_HD void decode_action(const QsParams& P, int act_type, const float a[4], cons
     } else if (act_type == QS_ACT_RAW_RPM) {                                         // CtrlAviary.py:140
 #pragma unroll
         for (int i = 0; i < 4; ++i) rpm[i] = clampd((double)a[i], 0.0, P.max_rpm);
-    } else {
+    } else if (PIDACT) {
         double tpx, tpy, tpz, tyaw = 0.0, tvx = 0.0, tvy = 0.0, tvz = 0.0;
         if (act_type == QS_ACT_PID) {                                                // :194-207, _calculateNextStep :1108-1150
             const double dx = (double)a[0] - d.px, dy = (double)a[1] - d.py, dz = (double)a[2] - d.pz;

@@ -87,11 +87,72 @@ __device__ __forceinline__ void init_drone(const QsState& st, long long tbl, qs:
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Row writer: the CTA's rows [c0, c0+rows) of obs are one contiguous span.  Lane = column (V = float4 when the
+// action is 4 wide, so one 18-lane instruction moves a whole 72-float row), warps stride over rows, and U
+// independent loads are issued before the first store so the L2 round trip is paid once per U rows.
+//   column c <  12/W            : kinematic head staged in shared memory by the owning thread
+//   12/W <= c < cols - A/W      : prev_obs column c + A/W   (history shifted by one action)
+//   c >= cols - A/W             : this tick's action
+// Row modes (autoreset): bit0 keep history unshifted, bit1 mirror the row into final_obs, bit2 zero history in obs.
+// ---------------------------------------------------------------------------------------------------------
+template <typename V, int W, int U>
+__device__ __forceinline__ void write_rows(const StepArgs& a, long long c0, int rows, const float* head_s, const float* act_s,
+                                           const unsigned char* mode_s) {
+    const int cols = a.obs_dim / W, hcols = 12 / W, acols = a.A / W, hist_end = cols - acols;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int iters = (cols + 31) >> 5;
+    const int my_rows = rows > warp ? (rows - warp + nwarps - 1) / nwarps : 0;
+    const int nitems = my_rows * iters;
+    const V* prev = reinterpret_cast<const V*>(a.io.obs_prev);
+    V* out = reinterpret_cast<V*>(a.io.obs);
+    V* fin = reinterpret_cast<V*>(a.io.final_obs);
+    const V* head = reinterpret_cast<const V*>(head_s);
+    for (int m0 = 0; m0 < nitems; m0 += U) {
+        V v[U];
+        long long dst[U];
+        unsigned char md[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int m = m0 + u;
+            dst[u] = -1;
+            md[u] = 0;
+            if (m < nitems) {
+                const int rr = m / iters, ci = m - rr * iters;
+                const int r = warp + rr * nwarps, c = (ci << 5) + lane;
+                if (c < cols) {
+                    const long long row = (c0 + r) * (long long)cols;
+                    const unsigned char mode = mode_s[r];
+                    dst[u] = row + c;
+                    if (c < hcols) {
+                        v[u] = head[r * hcols + c];
+                    } else {
+                        md[u] = mode | 8;
+                        const bool keep = mode & 1;
+                        if (c < hist_end || keep) v[u] = __ldg(prev + row + c + (keep ? 0 : acols));
+                        else v[u] = reinterpret_cast<const V*>(act_s + 4 * r)[c - hist_end];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (dst[u] >= 0) {
+                if (md[u] & 2) fin[dst[u]] = v[u];
+                if (md[u] & 4) memset(&v[u], 0, sizeof(V));
+                out[dst[u]] = v[u];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Fused control tick.  RAW = CtrlAviary semantics (clip raw rpm, [N][20] state vectors out, no task).
 // Block = tpb threads, tpb a multiple of D (drones of one aviary never straddle CTAs) when D <= 128.
 // ---------------------------------------------------------------------------------------------------------
-template <int EFF, bool RAW>
-__global__ void __launch_bounds__(kMaxTPB) step_kernel(const __grid_constant__ StepArgs a) {
+// PIDACT = the action type runs the embedded DSLPIDControl (PID / VEL / ONE_D_PID): a separate instantiation keeps
+// the controller's registers out of the plain RPM kernels.
+template <int EFF, bool RAW, bool PIDACT>
+__global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QsParams& P = a.P;
     const int tpb = a.tpb, D = a.D, A = a.A;
@@ -123,7 +184,19 @@ __global__ void __launch_bounds__(kMaxTPB) step_kernel(const __grid_constant__ S
     double R_last[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     int sc = 0;
     bool pending = false;
-    const bool pid_act = (a.act_type == QS_ACT_PID || a.act_type == QS_ACT_VEL || a.act_type == QS_ACT_ONE_D_PID);
+    constexpr bool pid_act = PIDACT;
+
+    // The action history of this CTA's rows is one contiguous span of prev_obs: ask the memory system to pull it
+    // into L2 now, so that the row writer at the end of the kernel (after the physics) finds it there.
+    if (!RAW && t == 0 && a.io.obs && a.io.obs_prev && a.obs_dim > 12 && !(a.flags & QS_FLAG_SKIP_EPILOGUE)) {
+        const long long rows_ = (N - c0) < tpb ? (N - c0) : tpb;
+        const uintptr_t p0 = reinterpret_cast<uintptr_t>(a.io.obs_prev + c0 * a.obs_dim);
+        const uintptr_t beg = (p0 + 15) & ~(uintptr_t)15;
+        const uintptr_t end = (p0 + (uintptr_t)rows_ * a.obs_dim * 4) & ~(uintptr_t)15;
+        if (end > beg) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(beg), "r"((unsigned)(end - beg)) : "memory");
+        }
+    }
 
     if (live) {
         load_drone(a.st.planes, N, i, d);
@@ -156,7 +229,7 @@ __global__ void __launch_bounds__(kMaxTPB) step_kernel(const __grid_constant__ S
         if (a.flags & QS_FLAG_RPM_FROM_LAST) {
             rpm[0] = rpm_prev[0]; rpm[1] = rpm_prev[1]; rpm[2] = rpm_prev[2]; rpm[3] = rpm_prev[3];
         } else {
-            qs::decode_action(P, RAW ? (int)QS_ACT_RAW_RPM : a.act_type, act, d, cur_yaw, pst, rpm);
+            qs::decode_action<PIDACT>(P, RAW ? (int)QS_ACT_RAW_RPM : a.act_type, act, d, cur_yaw, pst, rpm);
         }
     }
 
@@ -288,28 +361,10 @@ __global__ void __launch_bounds__(kMaxTPB) step_kernel(const __grid_constant__ S
     if (RAW) {
         float* out = a.io.obs + c0 * 20;
         for (int j = t; j < rows * 20; j += blockDim.x) out[j] = head_s[j];
+    } else if (A == 4) {
+        write_rows<float4, 4, 8>(a, c0, rows, head_s, act_s, mode_s);
     } else {
-        const int od = a.obs_dim;
-        const int hist_end = od - A;                       // columns [12, hist_end) come from prev columns [12+A, od)
-        const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
-        for (int r = warp; r < rows; r += nwarps) {
-            const long long row = (c0 + r) * (long long)od;
-            const unsigned char mode = mode_s[r];
-            const bool keep = mode & 1;
-            const int shift = keep ? 0 : A;
-            for (int c = lane; c < od; c += 32) {
-                float v;
-                if (c < 12) {
-                    v = head_s[r * 12 + c];
-                } else {
-                    if (c < hist_end || keep) v = __ldg(a.io.obs_prev + row + c + shift);
-                    else v = act_s[4 * r + (c - hist_end)];
-                    if (mode & 2) a.io.final_obs[row + c] = v;
-                    if (mode & 4) v = 0.f;
-                }
-                a.io.obs[row + c] = v;
-            }
-        }
+        write_rows<float, 1, 8>(a, c0, rows, head_s, act_s, mode_s);
     }
 }
 
@@ -452,12 +507,12 @@ size_t step_smem_bytes() {
     return (size_t)kMaxTPB * 20 * 4 + (size_t)kMaxTPB * 4 * 4 + (size_t)kMaxTPB * 2 * 8 + (size_t)kMaxTPB * 3 * 8 + 3 * (size_t)kMaxTPB;
 }
 
-template <bool RAW>
+template <bool RAW, bool PIDACT>
 cudaError_t launch_step(const StepArgs& a, cudaStream_t s) {
     const int blocks = (int)((a.N + a.tpb - 1) / a.tpb);
     const int threads = ((a.tpb + 31) / 32) * 32;
     const size_t sm = step_smem_bytes();
-#define QS_CASE(E) case E: step_kernel<E, RAW><<<blocks, threads, sm, s>>>(a); break;
+#define QS_CASE(E) case E: step_kernel<E, RAW, PIDACT><<<blocks, threads, sm, s>>>(a); break;
     switch (a.effects & 7u) {
         QS_CASE(0) QS_CASE(1) QS_CASE(2) QS_CASE(3) QS_CASE(4) QS_CASE(5) QS_CASE(6) QS_CASE(7)
     }
@@ -535,7 +590,7 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
     a.tpb = block_size_for(drones_per_env);
     a.counter_inc = io->tick_substeps > 0 ? io->tick_substeps : substeps;
     a.effects = effects; a.flags = flags;
-    const cudaError_t e = launch_step<false>(a, (cudaStream_t)stream);
+    const cudaError_t e = pid_act ? launch_step<false, true>(a, (cudaStream_t)stream) : launch_step<false, false>(a, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_step launch");
 }
 
@@ -559,7 +614,7 @@ int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, floa
     a.tpb = block_size_for(drones_per_env);
     a.counter_inc = substeps;
     a.effects = effects; a.flags = flags & QS_FLAG_RPY_F32;
-    const cudaError_t e = launch_step<true>(a, (cudaStream_t)stream);
+    const cudaError_t e = launch_step<true, false>(a, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_dyn_substeps launch");
 }
 

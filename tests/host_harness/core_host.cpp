@@ -40,7 +40,7 @@ void tick_all(const QsParams& P, float* planes, int n, const float* act, int A, 
         double rpm[4], rpm_prev[4] = {last_rpm[4 * i], last_rpm[4 * i + 1], last_rpm[4 * i + 2], last_rpm[4 * i + 3]};
         double yaw = 0, r_, p_;
         if (act_type == QS_ACT_VEL) qs::quat_to_euler<false>(d.qx, d.qy, d.qz, d.qw, r_, p_, yaw);
-        qs::decode_action(P, act_type, a, d, yaw, ps, rpm);
+        qs::decode_action<true>(P, act_type, a, d, yaw, ps, rpm);
         double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         qs::dyn_tick<EFF>(P, d, rpm, rpm_prev, 0.0, substeps, R);
         qs::Derived o; qs::derive<false>(d, R, o);
