@@ -31,7 +31,7 @@ _d = C.c_double
 
 class QsParams(C.Structure):
     _fields_ = [
-        ("dt", _d), ("ctrl_dt", _d), ("pyb_freq", _d), ("m", _d), ("gravity", _d), ("kf", _d), ("km", _d),
+        ("dt", _d), ("ctrl_dt", _d), ("pyb_freq", _d), ("m", _d), ("inv_m", _d), ("gravity", _d), ("kf", _d), ("km", _d),
         ("j", _d * 3), ("j_inv", _d * 3), ("hover_rpm", _d), ("max_rpm", _d),
         ("sx", _d * 4), ("sy", _d * 4), ("sz", _d * 4), ("kx", _d), ("ky", _d),
         ("gnd_eff_coeff", _d), ("prop_radius", _d), ("gnd_eff_h_clip", _d), ("prop_xyz", (_d * 3) * 4),

@@ -162,6 +162,7 @@ template <int EFF>
 QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const double rpm_prev[4], double dw_fz,
                     int substeps, double R_last[9]) {
     const double dt = P.dt;
+    const double dt_m = dt * P.inv_m;                                                // v += dt * (F / M)  (:858,:860)
     double f[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) f[i] = rpm[i] * rpm[i] * P.kf;                       // :838
@@ -177,19 +178,34 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
         const double k = 2.0 * 3.14159265358979323846;
         drag_sum = k * rpm_prev[0] / 60.0 + k * rpm_prev[1] / 60.0 + k * rpm_prev[2] / 60.0 + k * rpm_prev[3] / 60.0;
     }
+    // Unit quaternion on entry: the planes hold a float32-rounded unit quaternion (|q|^2 = 1 +- 1e-7); after this
+    // |q|^2 - 1 ~ 1e-16 for the whole tick (_integrateQ is norm preserving), so Bullet's s = 2/|q|^2 is evaluated as
+    // 2(2 - |q|^2), exact to (|q|^2-1)^2 -- one DFMA instead of a double-precision division per substep.
+    {
+        const double n2 = d.qx * d.qx + d.qy * d.qy + d.qz * d.qz + d.qw * d.qw;
+        const double inv = 1.0 / sqrt(n2);
+        d.qx *= inv; d.qy *= inv; d.qz *= inv; d.qw *= inv;
+    }
+    double q0x = d.qx, q0y = d.qy, q0z = d.qz, q0w = d.qw;                           // attitude at the start of the last substep
     for (int s = 0; s < substeps; ++s) {
-        double R[9];
-        quat_to_matrix(d.qx, d.qy, d.qz, d.qw, R);                                   // :836
+        q0x = d.qx; q0y = d.qy; q0z = d.qz; q0w = d.qw;
+        const double x = d.qx, y = d.qy, z = d.qz, w = d.qw;
+        const double dd = x * x + y * y + z * z + w * w;
+        const double sc = 2.0 * (2.0 - dd);                                          // = 2/|q|^2  (:836, Bullet setRotation)
+        const double xs = x * sc, ys = y * sc, zs = z * sc;
+        // third column and third row of R
+        const double r02 = x * zs + w * ys, r12 = y * zs - w * xs, r22 = 1.0 - (x * xs + y * ys);
         if (EFF & QS_EFFECT_GND) {                                                   // :715-750 on the substep-start state
-            const double sarg = -2.0 * (d.qx * d.qz - d.qw * d.qy);
-            const double ra = 2.0 * (d.qy * d.qz + d.qw * d.qx);
-            const double rb = d.qw * d.qw - d.qx * d.qx - d.qy * d.qy + d.qz * d.qz;
+            const double r20 = x * zs - w * ys, r21 = y * zs + w * xs;
+            const double sarg = -2.0 * (x * z - w * y);
+            const double ra = 2.0 * (y * z + w * x);
+            const double rb = w * w - x * x - y * y + z * z;
             // |roll| < pi/2 and |pitch| < pi/2 (:742) without trig: roll = atan2(ra, rb), pitch = asin(sarg) w/ guard
             const bool upright = (sarg > -0.99999) && (sarg < 0.99999) && (rb > 0.0 || (rb == 0.0 && ra == 0.0));
             double g[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const double hz = d.pz + R[6] * P.prop_xyz[i][0] + R[7] * P.prop_xyz[i][1] + R[8] * P.prop_xyz[i][2];
+                const double hz = d.pz + r20 * P.prop_xyz[i][0] + r21 * P.prop_xyz[i][1] + r22 * P.prop_xyz[i][2];
                 const double h = hz < P.gnd_eff_h_clip ? P.gnd_eff_h_clip : hz;       // :739-740
                 const double rr = P.prop_radius / (4.0 * h);
                 g[i] = upright ? rpm[i] * rpm[i] * P.kf * P.gnd_eff_coeff * (rr * rr) : 0.0;   // :741
@@ -199,7 +215,7 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
             tx = (P.sx[0] * f0 + P.sx[1] * f1 + P.sx[2] * f2 + P.sx[3] * f3) * P.kx;
             ty = (P.sy[0] * f0 + P.sy[1] * f1 + P.sy[2] * f2 + P.sy[3] * f3) * P.ky;
         }
-        double fx = R[2] * thrust, fy = R[5] * thrust, fz = R[8] * thrust - P.gravity;   // :840-841
+        double fx = r02 * thrust, fy = r12 * thrust, fz = r22 * thrust - P.gravity;  // :840-841
         if (EFF & QS_EFFECT_DRAG) {                                                  // world force = -DRAG_COEFF*sum (.) vel
             fx += (-1.0 * P.drag_coeff[0] * drag_sum) * d.vx;
             fy += (-1.0 * P.drag_coeff[1] * drag_sum) * d.vy;
@@ -209,15 +225,15 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
                 drag_sum = k * rpm[0] / 60.0 + k * rpm[1] / 60.0 + k * rpm[2] / 60.0 + k * rpm[3] / 60.0;
             }
         }
-        if (EFF & QS_EFFECT_DW) { fx += R[2] * dw_fz; fy += R[5] * dw_fz; fz += R[8] * dw_fz; }
+        if (EFF & QS_EFFECT_DW) { fx += r02 * dw_fz; fy += r12 * dw_fz; fz += r22 * dw_fz; }
         // torques - w x (J w)  (:856), w' = J^-1 torques (:857)
         const double jwx = P.j[0] * d.wx, jwy = P.j[1] * d.wy, jwz = P.j[2] * d.wz;
         const double ttx = tx - (d.wy * jwz - d.wz * jwy);
         const double tty = ty - (d.wz * jwx - d.wx * jwz);
         const double ttz = tz - (d.wx * jwy - d.wy * jwx);
-        d.vx = d.vx + dt * (fx / P.m);                                               // :858,:860
-        d.vy = d.vy + dt * (fy / P.m);
-        d.vz = d.vz + dt * (fz / P.m);
+        d.vx = d.vx + dt_m * fx;                                                     // :858,:860
+        d.vy = d.vy + dt_m * fy;
+        d.vz = d.vz + dt_m * fz;
         d.wx = d.wx + dt * (P.j_inv[0] * ttx);                                       // :861
         d.wy = d.wy + dt * (P.j_inv[1] * tty);
         d.wz = d.wz + dt * (P.j_inv[2] * ttz);
@@ -225,11 +241,8 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
         d.py = d.py + dt * d.vy;
         d.pz = d.pz + dt * d.vz;
         integrate_q(d, dt);                                                          // :863
-        if (s == substeps - 1) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) R_last[i] = R[i];
-        }
     }
+    quat_to_matrix(q0x, q0y, q0z, q0w, R_last);                                      // R used by :873 (ang_v = R_old w_new)
 }
 
 template <bool RPY_F32>

@@ -100,46 +100,42 @@ __device__ __forceinline__ void write_rows(const StepArgs& a, long long c0, int 
                                            const unsigned char* mode_s) {
     const int cols = a.obs_dim / W, hcols = 12 / W, acols = a.A / W, hist_end = cols - acols;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int iters = (cols + 31) >> 5;
-    const int my_rows = rows > warp ? (rows - warp + nwarps - 1) / nwarps : 0;
-    const int nitems = my_rows * iters;
-    const V* prev = reinterpret_cast<const V*>(a.io.obs_prev);
-    V* out = reinterpret_cast<V*>(a.io.obs);
-    V* fin = reinterpret_cast<V*>(a.io.final_obs);
+    // CTA-relative 32-bit offsets (a CTA's span is < 2^31 elements); one 64-bit base per buffer
+    const V* prev = reinterpret_cast<const V*>(a.io.obs_prev) + c0 * cols;
+    V* out = reinterpret_cast<V*>(a.io.obs) + c0 * cols;
+    V* fin = reinterpret_cast<V*>(a.io.final_obs) + c0 * cols;
     const V* head = reinterpret_cast<const V*>(head_s);
-    for (int m0 = 0; m0 < nitems; m0 += U) {
-        V v[U];
-        long long dst[U];
-        unsigned char md[U];
+    for (int cb = 0; cb < cols; cb += 32) {                   // column block (one iteration when the row fits 32 lanes)
+        const int c = cb + lane;
+        const bool col_ok = c < cols;
+        for (int r0 = warp; r0 < rows; r0 += nwarps * U) {
+            V v[U];
+            unsigned char md[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int m = m0 + u;
-            dst[u] = -1;
-            md[u] = 0;
-            if (m < nitems) {
-                const int rr = m / iters, ci = m - rr * iters;
-                const int r = warp + rr * nwarps, c = (ci << 5) + lane;
-                if (c < cols) {
-                    const long long row = (c0 + r) * (long long)cols;
+            for (int u = 0; u < U; ++u) {
+                const int r = r0 + u * nwarps;
+                md[u] = 0x80;                                  // 0x80 = nothing to store
+                if (r < rows && col_ok) {
                     const unsigned char mode = mode_s[r];
-                    dst[u] = row + c;
                     if (c < hcols) {
                         v[u] = head[r * hcols + c];
+                        md[u] = 0;
                     } else {
-                        md[u] = mode | 8;
+                        md[u] = mode;
                         const bool keep = mode & 1;
-                        if (c < hist_end || keep) v[u] = __ldg(prev + row + c + (keep ? 0 : acols));
+                        if (c < hist_end || keep) v[u] = __ldg(prev + r * cols + c + (keep ? 0 : acols));
                         else v[u] = reinterpret_cast<const V*>(act_s + 4 * r)[c - hist_end];
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (dst[u] >= 0) {
-                if (md[u] & 2) fin[dst[u]] = v[u];
-                if (md[u] & 4) memset(&v[u], 0, sizeof(V));
-                out[dst[u]] = v[u];
+            for (int u = 0; u < U; ++u) {
+                if (!(md[u] & 0x80)) {
+                    const int o = (r0 + u * nwarps) * cols + c;
+                    if (md[u] & 2) fin[o] = v[u];
+                    if (md[u] & 4) memset(&v[u], 0, sizeof(V));
+                    out[o] = v[u];
+                }
             }
         }
     }

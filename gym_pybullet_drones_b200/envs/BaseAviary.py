@@ -67,7 +67,7 @@ class BaseAviary(Env):
                  autoreset=None,
                  autoreset_clears_controllers=False,
                  autoreset_clears_action_buffer=False,
-                 rpy_f32=False,
+                 rpy_f32=True,
                  host_copy=True,
                  ):
         """Same positional/keyword parameters as the reference (BaseAviary.py:25-40).
@@ -84,7 +84,8 @@ class BaseAviary(Env):
             The reference's reset() clears neither the embedded PID controllers nor the action
             buffer (quirk kept by default); set to clear them when an env auto-resets.
         rpy_f32 : bool
-            Evaluate the reported roll/pitch/yaw with float32 atan2/asin (faster, ~2e-7 rad).
+            Evaluate the reported roll/pitch/yaw with float32 atan2f/asinf on float64 arguments (default; error ~2e-7 rad,
+            far inside the 1e-5 parity bound); False = float64 atan2/asin.
         host_copy : bool
             NumPy mode only: return fresh arrays (True) or views of the pinned staging buffers
             that stay valid until the next-but-one step (False).

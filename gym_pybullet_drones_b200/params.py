@@ -118,7 +118,7 @@ def fill_params(c, *, episode_len_sec=8.0, xy_bound=1.5, z_bound=2.0, tilt_bound
     """Packs an AviaryConstants (+ task and controller constants) into the C-ABI QsParams."""
     P = N.QsParams()
     P.dt, P.ctrl_dt, P.pyb_freq = c.PYB_TIMESTEP, c.CTRL_TIMESTEP, float(c.PYB_FREQ)
-    P.m, P.gravity, P.kf, P.km = c.M, c.GRAVITY, c.KF, c.KM
+    P.m, P.inv_m, P.gravity, P.kf, P.km = c.M, 1.0 / c.M, c.GRAVITY, c.KF, c.KM
     for k in range(3):
         P.j[k] = c.J[k, k]
         P.j_inv[k] = c.J_INV[k, k]

@@ -76,6 +76,7 @@ typedef struct QsParams {
     double ctrl_dt;        /* CTRL_TIMESTEP = 1/ctrl_freq                    BaseAviary.py:82 */
     double pyb_freq;       /* PYB_FREQ (for the time-out test)               HoverAviary.py:113 */
     double m;              /* M                                              cf2x.urdf:11 */
+    double inv_m;          /* 1/M (host-computed; the kernels multiply instead of dividing, BaseAviary.py:858) */
     double gravity;        /* GRAVITY = G*M                                  BaseAviary.py:117 */
     double kf, km;         /* KF, KM                                         cf2x.urdf:5 */
     double j[3];           /* diag(J)                                        cf2x.urdf:12 */
