@@ -58,7 +58,7 @@ class QsState(C.Structure):
 class QsStepIO(C.Structure):
     _fields_ = [
         ("action", C.c_void_p), ("obs_prev", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
-        ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("final_obs", C.c_void_p), ("dw_fz", C.c_void_p),
+        ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("final_obs", C.c_void_p), ("done", C.c_void_p), ("dw_fz", C.c_void_p),
         ("act_buffer_size", C.c_int), ("tick_substeps", C.c_int),
     ]
 

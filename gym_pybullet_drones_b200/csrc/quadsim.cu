@@ -33,6 +33,9 @@ int cuda_fail(cudaError_t e, const char* where) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kMaxTPB = 128;          // threads (= drones) per CTA upper bound
+// fixed part of the step kernel's dynamic shared memory (heads, actions, reductions, in-CTA downwash positions, flags,
+// mbarrier), rounded so that the staged rows that follow are 128-byte aligned
+constexpr size_t kStepSmemFixed = ((size_t)kMaxTPB * 20 * 4 + (size_t)kMaxTPB * 4 * 4 + (size_t)kMaxTPB * 2 * 8 + (size_t)kMaxTPB * 3 * 8 + 3 * (size_t)kMaxTPB + 16 + 127) / 128 * 128;
 
 struct StepArgs {
     QsParams P;
@@ -40,6 +43,8 @@ struct StepArgs {
     QsStepIO io;
     int act_type, task, n_envs, D, substeps, N, A, obs_dim, tpb, counter_inc;
     unsigned effects, flags;
+    int stage_rows;      // 1: the CTA's prev_obs rows are staged in shared memory by one TMA bulk copy
+    int pad_;
 };
 
 __device__ __forceinline__ float4 ldg4(const float* base, long long idx4) {
@@ -53,6 +58,25 @@ __device__ __forceinline__ void st4(float* base, long long idx4, float4 v) {
 __device__ __forceinline__ void split2(double v, float& hi, float& lo) {
     hi = (float)v;
     lo = (float)(v - (double)hi);
+}
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier: one thread moves a whole contiguous span global -> shared
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
 }
 
 __device__ __forceinline__ void load_drone(const float* planes, long long N, long long i, qs::Drone& d) {
@@ -97,7 +121,7 @@ __device__ __forceinline__ void init_drone(const QsState& st, long long tbl, qs:
 // ---------------------------------------------------------------------------------------------------------
 template <typename V, int W, int U>
 __device__ __forceinline__ void write_rows(const StepArgs& a, long long c0, int rows, const float* head_s, const float* act_s,
-                                           const unsigned char* mode_s) {
+                                           const unsigned char* mode_s, const float* stage_s) {
     const int cols = a.obs_dim / W, hcols = 12 / W, acols = a.A / W, hist_end = cols - acols;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // CTA-relative 32-bit offsets (a CTA's span is < 2^31 elements); one 64-bit base per buffer
@@ -105,6 +129,7 @@ __device__ __forceinline__ void write_rows(const StepArgs& a, long long c0, int 
     V* out = reinterpret_cast<V*>(a.io.obs) + c0 * cols;
     V* fin = reinterpret_cast<V*>(a.io.final_obs) + c0 * cols;
     const V* head = reinterpret_cast<const V*>(head_s);
+    const V* stage = reinterpret_cast<const V*>(stage_s);     // prev rows already in shared memory (TMA) or nullptr
     for (int cb = 0; cb < cols; cb += 32) {                   // column block (one iteration when the row fits 32 lanes)
         const int c = cb + lane;
         const bool col_ok = c < cols;
@@ -123,7 +148,10 @@ __device__ __forceinline__ void write_rows(const StepArgs& a, long long c0, int 
                     } else {
                         md[u] = mode;
                         const bool keep = mode & 1;
-                        if (c < hist_end || keep) v[u] = __ldg(prev + r * cols + c + (keep ? 0 : acols));
+                        if (c < hist_end || keep) {
+                            const int so = r * cols + c + (keep ? 0 : acols);
+                            v[u] = stage ? stage[so] : __ldg(prev + so);
+                        }
                         else v[u] = reinterpret_cast<const V*>(act_s + 4 * r)[c - hist_end];
                     }
                 }
@@ -166,6 +194,8 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
     unsigned char* oob_s = reinterpret_cast<unsigned char*>(pos_s + (size_t)kMaxTPB * 3);   // [tpb]
     unsigned char* mode_s = oob_s + kMaxTPB;                             // [tpb] row mode: 0 shift, 1 keep history, 2 also final_obs
     unsigned char* done_s = mode_s + kMaxTPB;                            // [tpb] per local env
+    unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(smem_raw + kStepSmemFixed - 16);   // mbarrier of the row staging
+    float* stage_s = a.stage_rows ? reinterpret_cast<float*>(smem_raw + kStepSmemFixed) : nullptr;       // [tpb][obs_dim]
 
     const long long e = live ? i / D : 0;
     const int le = t / D;                                      // local env (meaningful when D <= tpb)
@@ -182,9 +212,18 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
     bool pending = false;
     constexpr bool pid_act = PIDACT;
 
-    // The action history of this CTA's rows is one contiguous span of prev_obs: ask the memory system to pull it
-    // into L2 now, so that the row writer at the end of the kernel (after the physics) finds it there.
-    if (!RAW && t == 0 && a.io.obs && a.io.obs_prev && a.obs_dim > 12 && !(a.flags & QS_FLAG_SKIP_EPILOGUE)) {
+    // The action history of this CTA's rows is one contiguous span of prev_obs.  When it fits, ONE thread starts a TMA
+    // bulk copy of the whole span into shared memory now (completion on an mbarrier); the physics below runs while it is
+    // in flight and the row writer at the end reads it from shared memory.  Otherwise the span is at least pulled into L2.
+    const bool want_rows = !RAW && a.io.obs && a.io.obs_prev && a.obs_dim > 12 && !(a.flags & QS_FLAG_SKIP_EPILOGUE);
+    if (want_rows && a.stage_rows) {
+        if (t == 0) mbar_init(bar_s, 1);
+        __syncthreads();
+        if (t == 0) {
+            const long long rows_ = (N - c0) < tpb ? (N - c0) : tpb;
+            tma_bulk_g2s(stage_s, a.io.obs_prev + c0 * a.obs_dim, (unsigned)(rows_ * a.obs_dim * 4), bar_s);
+        }
+    } else if (want_rows && t == 0) {
         const long long rows_ = (N - c0) < tpb ? (N - c0) : tpb;
         const uintptr_t p0 = reinterpret_cast<uintptr_t>(a.io.obs_prev + c0 * a.obs_dim);
         const uintptr_t beg = (p0 + 15) & ~(uintptr_t)15;
@@ -280,12 +319,14 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
             a.io.reward[e] = (float)rew;
             a.io.terminated[e] = term ? 1 : 0;
             a.io.truncated[e] = trunc ? 1 : 0;
+            if (a.io.done) a.io.done[e] = (term || trunc) ? 1 : 0;
             done_s[le] = (term || trunc) ? 1 : 0;
         }
         __syncthreads();
         if (live) env_done = done_s[le] != 0;
     } else if (!RAW && want_epilogue && live && dslot == 0) {
         a.io.reward[e] = -1.0f; a.io.terminated[e] = 0; a.io.truncated[e] = 0;     // CtrlAviary-style dummy task
+        if (a.io.done) a.io.done[e] = 0;
     }
 
     // ---- stage this drone's row head, autoreset, store state ---------------------------------------------
@@ -351,6 +392,7 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
     }
     if (a.io.obs == nullptr || !want_epilogue) return;
     __syncthreads();
+    if (want_rows && a.stage_rows) mbar_wait(bar_s, 0);
 
     // ---- cooperative, coalesced write of this CTA's observation rows --------------------------------------
     const int rows = (int)((N - c0) < tpb ? (N - c0) : tpb);
@@ -358,9 +400,9 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
         float* out = a.io.obs + c0 * 20;
         for (int j = t; j < rows * 20; j += blockDim.x) out[j] = head_s[j];
     } else if (A == 4) {
-        write_rows<float4, 4, 8>(a, c0, rows, head_s, act_s, mode_s);
+        write_rows<float4, 4, 8>(a, c0, rows, head_s, act_s, mode_s, stage_s);
     } else {
-        write_rows<float, 1, 8>(a, c0, rows, head_s, act_s, mode_s);
+        write_rows<float, 1, 8>(a, c0, rows, head_s, act_s, mode_s, stage_s);
     }
 }
 
@@ -499,16 +541,27 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ Rese
     }
 }
 
-size_t step_smem_bytes() {
-    return (size_t)kMaxTPB * 20 * 4 + (size_t)kMaxTPB * 4 * 4 + (size_t)kMaxTPB * 2 * 8 + (size_t)kMaxTPB * 3 * 8 + 3 * (size_t)kMaxTPB;
+constexpr size_t kStageLimit = 40 * 1024;      // bytes of staged rows per CTA (4 CTAs/SM must fit in 227 KB)
+
+size_t step_smem_bytes(const StepArgs& a) {
+    return kStepSmemFixed + (a.stage_rows ? (size_t)a.tpb * a.obs_dim * 4 : 0);
 }
 
 template <bool RAW, bool PIDACT>
 cudaError_t launch_step(const StepArgs& a, cudaStream_t s) {
     const int blocks = (int)((a.N + a.tpb - 1) / a.tpb);
     const int threads = ((a.tpb + 31) / 32) * 32;
-    const size_t sm = step_smem_bytes();
-#define QS_CASE(E) case E: step_kernel<E, RAW, PIDACT><<<blocks, threads, sm, s>>>(a); break;
+    const size_t sm = step_smem_bytes(a);
+#define QS_CASE(E)                                                                                               \
+    case E: {                                                                                                    \
+        static bool attr_set = false;                                                                            \
+        if (!attr_set) {                                                                                         \
+            cudaFuncSetAttribute(step_kernel<E, RAW, PIDACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                 (int)(kStepSmemFixed + kStageLimit));                                           \
+            attr_set = true;                                                                                     \
+        }                                                                                                        \
+        step_kernel<E, RAW, PIDACT><<<blocks, threads, sm, s>>>(a);                                              \
+    } break;
     switch (a.effects & 7u) {
         QS_CASE(0) QS_CASE(1) QS_CASE(2) QS_CASE(3) QS_CASE(4) QS_CASE(5) QS_CASE(6) QS_CASE(7)
     }
@@ -586,6 +639,12 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
     a.tpb = block_size_for(drones_per_env);
     a.counter_inc = io->tick_substeps > 0 ? io->tick_substeps : substeps;
     a.effects = effects; a.flags = flags;
+    // TMA bulk staging of the CTA's prev_obs rows: needs 16-byte aligned span start/size for every CTA and a bounded footprint
+    {
+        const size_t row_bytes = (size_t)a.obs_dim * 4, span = row_bytes * a.tpb;
+        const bool aligned = aligned16(io->obs_prev) && (span % 16 == 0) && ((row_bytes * ((size_t)a.N % a.tpb)) % 16 == 0);
+        a.stage_rows = (io->obs && io->act_buffer_size > 0 && aligned && span <= kStageLimit) ? 1 : 0;
+    }
     const cudaError_t e = pid_act ? launch_step<false, true>(a, (cudaStream_t)stream) : launch_step<false, false>(a, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_step launch");
 }

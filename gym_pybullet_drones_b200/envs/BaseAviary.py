@@ -217,6 +217,7 @@ class BaseAviary(Env):
         self._reward = torch.zeros((E,), **f32)
         self._terminated = torch.zeros((E,), dtype=torch.bool, device=dev)
         self._truncated = torch.zeros((E,), dtype=torch.bool, device=dev)
+        self._done = torch.zeros((E,), dtype=torch.bool, device=dev)
         self._final_obs = torch.zeros((n, self._obs_dim), **f32) if (self._flags & N.FLAG_AUTORESET_SAME_STEP) else None
         big_dw = (self._effects & N.EFFECT_DW) and D > 128
         self._dw_fz = torch.zeros((n,), **f32) if big_dw else None
@@ -243,10 +244,20 @@ class BaseAviary(Env):
         io = N.QsStepIO()
         io.reward, io.terminated, io.truncated = self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr()
         io.final_obs = self._final_obs.data_ptr() if self._final_obs is not None else None
+        io.done = self._done.data_ptr()
         io.dw_fz = self._dw_fz.data_ptr() if self._dw_fz is not None else None
         io.act_buffer_size = self._B
         io.tick_substeps = 0
         self._io = io
+        #### pre-resolved handles for the per-step fast path ####
+        self._obs_ptr = [b.data_ptr() for b in self._obs_buf]
+        self._obs_view = [b.view(E, D, self._obs_dim) for b in self._obs_buf]
+        self._final_view = self._final_obs.view(E, D, self._obs_dim) if self._final_obs is not None else None
+        self._simple_launch = self._dw_fz is None and not raw
+        self._qs_step = self._lib.qs_step
+        self._step_head = (C.byref(self._P), C.byref(self._st), C.byref(io), self._act_type(), self._task(),
+                           E, D, self.PYB_STEPS_PER_CTRL, self._effects, self._flags)
+        self._dev_index = self.device.index
         #### pinned host staging for the NumPy API ####
         self._h_action = torch.zeros((n, self._A), dtype=torch.float32).pin_memory()
         self._h_obs = [torch.zeros((n, self._obs_dim), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -406,6 +417,27 @@ class BaseAviary(Env):
         Vector API: `action` is a float32 CUDA tensor [E, D, A] (used in place) or an ndarray (copied through a
         pinned buffer); returns tensors or ndarrays accordingly.  Single-env API: ndarray [D, A] in, the
         reference's 5-tuple out (BaseAviary.py:262-290)."""
+        if type(action) is torch.Tensor and self.VECTORIZED and self._simple_launch:
+            #### fast path: device tensor in, device tensors out, one kernel launch, no other device work ####
+            a = action
+            if a.dtype is not torch.float32 or a.device != self.device or not a.is_contiguous() or (a.data_ptr() & 15):
+                self._action_dev.copy_(a.reshape(self._N, self._A))
+                a = self._action_dev
+            if torch.cuda.current_device() != self._dev_index:
+                with self._on_device():
+                    return self.step(action)
+            io, cur = self._io, self._cur
+            io.action = a.data_ptr()
+            io.obs_prev = self._obs_ptr[cur]
+            io.obs = self._obs_ptr[1 - cur]
+            rc = self._qs_step(*self._step_head, torch.cuda.current_stream().cuda_stream)
+            if rc:
+                N.check(rc, "qs_step")
+            self._cur = cur = 1 - cur
+            if self._final_view is None:
+                return self._obs_view[cur], self._reward, self._terminated, self._truncated, {}
+            return (self._obs_view[cur], self._reward, self._terminated, self._truncated,
+                    {"final_obs": self._final_view, "_final_obs": self._done})
         with self._on_device():
             if isinstance(action, torch.Tensor):
                 a = action
@@ -420,7 +452,7 @@ class BaseAviary(Env):
                     return self._single_result(obs)
                 info = {}
                 if self._final_obs is not None:
-                    info = {"final_obs": self._final_obs.view(self._E, self._D, self._obs_dim), "_final_obs": self._terminated | self._truncated}
+                    info = {"final_obs": self._final_obs.view(self._E, self._D, self._obs_dim), "_final_obs": self._done}
                 return self._shape_obs(obs), self._reward, self._terminated, self._truncated, info
             #### NumPy path: pinned H2D of the action, D2H of the results, all inside this call ####
             a_np = np.asarray(action, dtype=np.float32).reshape(self._N, self._A)

@@ -138,6 +138,7 @@ typedef struct QsStepIO {
     unsigned char* terminated;  /* out [E] */
     unsigned char* truncated;   /* out [E] */
     float* final_obs;           /* out [N][obs_dim] rows of envs that finished, SAME_STEP autoreset only; nullable */
+    unsigned char* done;        /* out [E] terminated | truncated (the `_final_obs` mask of gymnasium's vector API); nullable */
     const float* dw_fz;         /* [N] downwash force along body z from qs_downwash; required iff QS_EFFECT_DW */
     int act_buffer_size;        /* B = ctrl_freq//2 (BaseRLAviary.py:66); 0 for RAW_RPM */
     int tick_substeps;          /* physics steps the step counter advances by in the epilogue; 0 = `substeps`
