@@ -79,6 +79,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     } while (!ok);
 }
 
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src_gmem) {      // LDGSTS, 4-byte granule
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ void load_drone(const float* planes, long long N, long long i, qs::Drone& d) {
     const float4 p0 = ldg4(planes, i), p1 = ldg4(planes, N + i), p2 = ldg4(planes, 2 * N + i), p3 = ldg4(planes, 3 * N + i);
     d.px = p0.x; d.py = p0.y; d.pz = p0.z;
@@ -212,22 +219,26 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
     bool pending = false;
     constexpr bool pid_act = PIDACT;
 
-    // The action history of this CTA's rows is one contiguous span of prev_obs.  When it fits, ONE thread starts a TMA
-    // bulk copy of the whole span into shared memory now (completion on an mbarrier); the physics below runs while it is
-    // in flight and the row writer at the end reads it from shared memory.  Otherwise the span is at least pulled into L2.
+    // The observation rows of this CTA are one contiguous span, and the new rows are the old ones shifted left by one
+    // action: new_flat[j] = old_flat[j + A] once every thread has patched its own row (head -> slots [A, A+12), new
+    // action -> the A slots after the row, i.e. the dead head slots of the next row).  So: ONE thread starts a TMA bulk
+    // copy of the old span into shared memory now (completion on an mbarrier), the physics below runs while it is in
+    // flight, then the span is streamed out with a flat, fully coalesced float4 copy.  Spans too large for shared
+    // memory are only pulled into L2 (and written by write_rows).
     const bool want_rows = !RAW && a.io.obs && a.io.obs_prev && a.obs_dim > 12 && !(a.flags & QS_FLAG_SKIP_EPILOGUE);
-    if (want_rows && a.stage_rows) {
+    const int rows = (int)((N - c0) < tpb ? (N - c0) : tpb);
+    if (want_rows && a.stage_rows == 1) {
         if (t == 0) mbar_init(bar_s, 1);
         __syncthreads();
-        if (t == 0) {
-            const long long rows_ = (N - c0) < tpb ? (N - c0) : tpb;
-            tma_bulk_g2s(stage_s, a.io.obs_prev + c0 * a.obs_dim, (unsigned)(rows_ * a.obs_dim * 4), bar_s);
-        }
+        if (t == 0) tma_bulk_g2s(stage_s, a.io.obs_prev + c0 * a.obs_dim, (unsigned)(rows * a.obs_dim * 4), bar_s);
+    } else if (want_rows && a.stage_rows == 2) {
+        // spans that are not 16-byte aligned (odd action widths): per-thread 4-byte async copies (LDGSTS), still fire-and-forget
+        const float* src = a.io.obs_prev + c0 * a.obs_dim;
+        for (int j = t; j < rows * a.obs_dim; j += blockDim.x) cp_async4(stage_s + j, src + j);
     } else if (want_rows && t == 0) {
-        const long long rows_ = (N - c0) < tpb ? (N - c0) : tpb;
         const uintptr_t p0 = reinterpret_cast<uintptr_t>(a.io.obs_prev + c0 * a.obs_dim);
         const uintptr_t beg = (p0 + 15) & ~(uintptr_t)15;
-        const uintptr_t end = (p0 + (uintptr_t)rows_ * a.obs_dim * 4) & ~(uintptr_t)15;
+        const uintptr_t end = (p0 + (uintptr_t)rows * a.obs_dim * 4) & ~(uintptr_t)15;
         if (end > beg) {
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(beg), "r"((unsigned)(end - beg)) : "memory");
         }
@@ -391,18 +402,55 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
         }
     }
     if (a.io.obs == nullptr || !want_epilogue) return;
+    const int od = a.obs_dim;
+    if (want_rows && a.stage_rows) {
+        // ---- staged rows: wait for the async copy, patch my row in shared memory, stream the span out ----------
+        if (a.stage_rows == 1) mbar_wait(bar_s, 0); else cp_async_commit_wait_all();
+        __syncthreads();
+        if (live) {
+            float* row = stage_s + (size_t)t * od;
+            const float* h = head_s + (size_t)t * 12;
+            const unsigned char mode = mode_s[t];
+            if (mode & 1) {                                   // NEXT_STEP reset tick: history is NOT shifted
+                for (int k = od - 1; k >= 12; --k) row[k + A] = row[k];
+            } else {
+                for (int k = 0; k < A; ++k) row[od + k] = act[k];
+            }
+            if (A == 4) {
+                float4* r4 = reinterpret_cast<float4*>(row + 4);
+                r4[0] = make_float4(h[0], h[1], h[2], h[3]); r4[1] = make_float4(h[4], h[5], h[6], h[7]); r4[2] = make_float4(h[8], h[9], h[10], h[11]);
+            } else {
+                for (int k = 0; k < 12; ++k) row[A + k] = h[k];
+            }
+            if (mode & 2) {                                   // SAME_STEP autoreset: terminal observation's history
+                float* f = a.io.final_obs + i * od;
+                for (int k = 12; k < od; ++k) f[k] = row[k + A];
+            }
+            if (mode & 4) for (int k = 12; k < od; ++k) row[k + A] = 0.f;
+        }
+        __syncthreads();
+        if (A == 4) {
+            const float4* src = reinterpret_cast<const float4*>(stage_s) + 1;
+            float4* out = reinterpret_cast<float4*>(a.io.obs + c0 * od);
+            const int n4 = rows * (od >> 2);
+            for (int j = t; j < n4; j += blockDim.x) out[j] = src[j];
+        } else {
+            const float* src = stage_s + A;
+            float* out = a.io.obs + c0 * od;
+            for (int j = t; j < rows * od; j += blockDim.x) out[j] = src[j];
+        }
+        return;
+    }
     __syncthreads();
-    if (want_rows && a.stage_rows) mbar_wait(bar_s, 0);
 
-    // ---- cooperative, coalesced write of this CTA's observation rows --------------------------------------
-    const int rows = (int)((N - c0) < tpb ? (N - c0) : tpb);
+    // ---- cooperative, coalesced write of this CTA's observation rows (unstaged paths) -----------------------------
     if (RAW) {
         float* out = a.io.obs + c0 * 20;
         for (int j = t; j < rows * 20; j += blockDim.x) out[j] = head_s[j];
     } else if (A == 4) {
-        write_rows<float4, 4, 8>(a, c0, rows, head_s, act_s, mode_s, stage_s);
+        write_rows<float4, 4, 8>(a, c0, rows, head_s, act_s, mode_s, nullptr);
     } else {
-        write_rows<float, 1, 8>(a, c0, rows, head_s, act_s, mode_s, stage_s);
+        write_rows<float, 1, 8>(a, c0, rows, head_s, act_s, mode_s, nullptr);
     }
 }
 
@@ -544,7 +592,7 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ Rese
 constexpr size_t kStageLimit = 40 * 1024;      // bytes of staged rows per CTA (4 CTAs/SM must fit in 227 KB)
 
 size_t step_smem_bytes(const StepArgs& a) {
-    return kStepSmemFixed + (a.stage_rows ? (size_t)a.tpb * a.obs_dim * 4 : 0);
+    return kStepSmemFixed + (a.stage_rows ? (size_t)a.tpb * a.obs_dim * 4 + 32 : 0);
 }
 
 template <bool RAW, bool PIDACT>
@@ -557,7 +605,7 @@ cudaError_t launch_step(const StepArgs& a, cudaStream_t s) {
         static bool attr_set = false;                                                                            \
         if (!attr_set) {                                                                                         \
             cudaFuncSetAttribute(step_kernel<E, RAW, PIDACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                 (int)(kStepSmemFixed + kStageLimit));                                           \
+                                 (int)(kStepSmemFixed + kStageLimit + 32));                                           \
             attr_set = true;                                                                                     \
         }                                                                                                        \
         step_kernel<E, RAW, PIDACT><<<blocks, threads, sm, s>>>(a);                                              \
@@ -639,11 +687,13 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
     a.tpb = block_size_for(drones_per_env);
     a.counter_inc = io->tick_substeps > 0 ? io->tick_substeps : substeps;
     a.effects = effects; a.flags = flags;
-    // TMA bulk staging of the CTA's prev_obs rows: needs 16-byte aligned span start/size for every CTA and a bounded footprint
+    // staging of the CTA's prev_obs rows in shared memory: TMA bulk copy when every CTA's span is 16-byte aligned and sized,
+    // per-thread LDGSTS otherwise; none when the span does not fit (e.g. 240 Hz control: 120-action buffers)
     {
         const size_t row_bytes = (size_t)a.obs_dim * 4, span = row_bytes * a.tpb;
-        const bool aligned = aligned16(io->obs_prev) && (span % 16 == 0) && ((row_bytes * ((size_t)a.N % a.tpb)) % 16 == 0);
-        a.stage_rows = (io->obs && io->act_buffer_size > 0 && aligned && span <= kStageLimit) ? 1 : 0;
+        const bool aligned = aligned16(io->obs_prev) && aligned16(io->obs) && (span % 16 == 0) && ((row_bytes * ((size_t)a.N % a.tpb)) % 16 == 0);
+        a.stage_rows = 0;
+        if (io->obs && io->act_buffer_size > 0 && span <= kStageLimit) a.stage_rows = (aligned && A == 4) ? 1 : 2;
     }
     const cudaError_t e = pid_act ? launch_step<false, true>(a, (cudaStream_t)stream) : launch_step<false, false>(a, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_step launch");
