@@ -183,7 +183,11 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
     // 2(2 - |q|^2), exact to (|q|^2-1)^2 -- one DFMA instead of a double-precision division per substep.
     {
         const double n2 = d.qx * d.qx + d.qy * d.qy + d.qz * d.qz + d.qw * d.qw;
+#if defined(__CUDA_ARCH__)
+        const double inv = rsqrt(n2);
+#else
         const double inv = 1.0 / sqrt(n2);
+#endif
         d.qx *= inv; d.qy *= inv; d.qz *= inv; d.qw *= inv;
     }
     double q0x = d.qx, q0y = d.qy, q0z = d.qz, q0w = d.qw;                           // attitude at the start of the last substep

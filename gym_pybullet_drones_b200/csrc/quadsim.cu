@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
     unsigned char* mode_s = oob_s + kMaxTPB;                             // [tpb] row mode: 0 shift, 1 keep history, 2 also final_obs
     unsigned char* done_s = mode_s + kMaxTPB;                            // [tpb] per local env
     unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(smem_raw + kStepSmemFixed - 16);   // mbarrier of the row staging
-    float* stage_s = a.stage_rows ? reinterpret_cast<float*>(smem_raw + kStepSmemFixed) : nullptr;       // [tpb][obs_dim]
+    float* stage_s = reinterpret_cast<float*>(smem_raw + kStepSmemFixed);                                // [tpb][obs_dim] (+A) when staged
 
     const long long e = live ? i / D : 0;
     const int le = t / D;                                      // local env (meaningful when D <= tpb)
@@ -230,18 +230,6 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
     if (want_rows && a.stage_rows == 1) {
         if (t == 0) mbar_init(bar_s, 1);
         __syncthreads();
-        if (t == 0) tma_bulk_g2s(stage_s, a.io.obs_prev + c0 * a.obs_dim, (unsigned)(rows * a.obs_dim * 4), bar_s);
-    } else if (want_rows && a.stage_rows == 2) {
-        // spans that are not 16-byte aligned (odd action widths): per-thread 4-byte async copies (LDGSTS), still fire-and-forget
-        const float* src = a.io.obs_prev + c0 * a.obs_dim;
-        for (int j = t; j < rows * a.obs_dim; j += blockDim.x) cp_async4(stage_s + j, src + j);
-    } else if (want_rows && t == 0) {
-        const uintptr_t p0 = reinterpret_cast<uintptr_t>(a.io.obs_prev + c0 * a.obs_dim);
-        const uintptr_t beg = (p0 + 15) & ~(uintptr_t)15;
-        const uintptr_t end = (p0 + (uintptr_t)rows * a.obs_dim * 4) & ~(uintptr_t)15;
-        if (end > beg) {
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(beg), "r"((unsigned)(end - beg)) : "memory");
-        }
     }
 
     if (live) {
@@ -249,8 +237,10 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
         if (A == 4) {
             const float4 v = ldg4(a.io.action, i);
             act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
+        } else if (A == 3) {
+            act[0] = __ldg(a.io.action + i * 3); act[1] = __ldg(a.io.action + i * 3 + 1); act[2] = __ldg(a.io.action + i * 3 + 2);
         } else {
-            for (int k = 0; k < A; ++k) act[k] = __ldg(a.io.action + i * A + k);
+            act[0] = __ldg(a.io.action + i);
         }
         if (((EFF & QS_EFFECT_DRAG) || (a.flags & QS_FLAG_RPM_FROM_LAST)) && a.st.last_rpm) {
             const float4 v = ldg4(a.st.last_rpm, i);
@@ -264,6 +254,23 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
         }
         sc = a.st.step_counter[e];
         if ((a.flags & QS_FLAG_AUTORESET_NEXT_STEP) && a.st.pending_reset) pending = a.st.pending_reset[e] != 0;
+    }
+
+    // async copy of the old observation span, issued AFTER this thread's state/action loads so that the small, latency
+    // critical loads are ahead of the 36 KB bulk transfer in the memory system
+    if (want_rows && a.stage_rows == 1) {
+        if (t == 0) tma_bulk_g2s(stage_s, a.io.obs_prev + c0 * a.obs_dim, (unsigned)(rows * a.obs_dim * 4), bar_s);
+    } else if (want_rows && a.stage_rows == 2) {
+        // spans that are not 16-byte aligned (odd action widths): per-thread 4-byte async copies (LDGSTS), still fire-and-forget
+        const float* src = a.io.obs_prev + c0 * a.obs_dim;
+        for (int j = t; j < rows * a.obs_dim; j += blockDim.x) cp_async4(stage_s + j, src + j);
+    } else if (want_rows && t == 0) {
+        const uintptr_t p0 = reinterpret_cast<uintptr_t>(a.io.obs_prev + c0 * a.obs_dim);
+        const uintptr_t beg = (p0 + 15) & ~(uintptr_t)15;
+        const uintptr_t end = (p0 + (uintptr_t)rows * a.obs_dim * 4) & ~(uintptr_t)15;
+        if (end > beg) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(beg), "r"((unsigned)(end - beg)) : "memory");
+        }
     }
 
     if (live && !pending) {
@@ -413,8 +420,12 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
             const unsigned char mode = mode_s[t];
             if (mode & 1) {                                   // NEXT_STEP reset tick: history is NOT shifted
                 for (int k = od - 1; k >= 12; --k) row[k + A] = row[k];
+            } else if (A == 4) {
+                *reinterpret_cast<float4*>(row + od) = make_float4(act[0], act[1], act[2], act[3]);
+            } else if (A == 3) {
+                row[od] = act[0]; row[od + 1] = act[1]; row[od + 2] = act[2];
             } else {
-                for (int k = 0; k < A; ++k) row[od + k] = act[k];
+                row[od] = act[0];
             }
             if (A == 4) {
                 float4* r4 = reinterpret_cast<float4*>(row + 4);
@@ -433,7 +444,13 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
             const float4* src = reinterpret_cast<const float4*>(stage_s) + 1;
             float4* out = reinterpret_cast<float4*>(a.io.obs + c0 * od);
             const int n4 = rows * (od >> 2);
-            for (int j = t; j < n4; j += blockDim.x) out[j] = src[j];
+            const int nt = blockDim.x;
+            int j = t;
+            for (; j + 5 * nt < n4; j += 6 * nt) {            // 6 independent LDS.128 in flight, then 6 coalesced STG.128
+                const float4 v0 = src[j], v1 = src[j + nt], v2 = src[j + 2 * nt], v3 = src[j + 3 * nt], v4 = src[j + 4 * nt], v5 = src[j + 5 * nt];
+                out[j] = v0; out[j + nt] = v1; out[j + 2 * nt] = v2; out[j + 3 * nt] = v3; out[j + 4 * nt] = v4; out[j + 5 * nt] = v5;
+            }
+            for (; j < n4; j += nt) out[j] = src[j];
         } else {
             const float* src = stage_s + A;
             float* out = a.io.obs + c0 * od;
