@@ -293,6 +293,38 @@ def main():
                                        "note": "same kernel launches captured once in a CUDA graph (16 steps per replay): no per-step host work"}
     except Exception as ex:  # pragma: no cover
         extras["cuda_graph_replay"] = {"error": repr(ex)}
+    if "ms_per_step" in extras.get("cuda_graph_replay", {}):
+        gms = extras["cuda_graph_replay"]["ms_per_step"]
+        if gms < roofline["kernel_ms"]:
+            # back-to-back launches of ONLY this kernel inside one CUDA graph: elapsed/K bounds the kernel duration from
+            # above without the ~3 us of event/launch gap that per-launch event pairs include
+            roofline.update(kernel_ms_event_pairs=roofline["kernel_ms"], kernel_ms=gms,
+                            achieved=ALG_BYTES * DRONES_PER_GPU / (gms * 1e-3) / 1e9,
+                            frac=ALG_BYTES * DRONES_PER_GPU / (gms * 1e-3) / 1e9 / peak_gbs,
+                            timing="CUDA events around K back-to-back graph-captured launches / K")
+    # the same kernel at sizes where several waves overlap load, compute and store (one batch, working set > L2)
+    sweep = {}
+    if world == 1:
+        for n in (262144, 1048576):
+            try:
+                big = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=n // D, device=dev, autoreset="same_step")
+                ba = torch.rand((n // D, D, A), device=dev, generator=gen) * 2 - 1
+                big.reset()
+                for _ in range(10):
+                    big.step(ba)
+                torch.cuda.synchronize()
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
+                for _ in range(100):
+                    big.step(ba)
+                b1.record()
+                torch.cuda.synchronize()
+                bms = b0.elapsed_time(b1) / 100
+                sweep[str(n)] = {"ms_per_step": bms, "value": n / (bms * 1e-3), "hbm_frac": ALG_BYTES * n / (bms * 1e-3) / 1e9 / peak_gbs}
+                del big, ba
+            except Exception as ex:  # pragma: no cover
+                sweep[str(n)] = {"error": repr(ex)}
+        extras["drones_per_launch_sweep"] = sweep
     tiny = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=64, device=dev, autoreset="same_step")
     ta = torch.zeros((64, D, A), device=dev)
     tiny.reset()

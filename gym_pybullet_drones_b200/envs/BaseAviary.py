@@ -264,7 +264,6 @@ class BaseAviary(Env):
         self._h_reward = [torch.zeros((E,), dtype=torch.float32).pin_memory() for _ in range(2)]
         self._h_term = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
         self._h_trunc = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
-        self._h_final = torch.zeros((n, self._obs_dim), dtype=torch.float32).pin_memory() if self._final_obs is not None else None
         self._hcur = 0
 
     ################################################################################
@@ -477,9 +476,13 @@ class BaseAviary(Env):
             if self._final_obs is not None:
                 done = term | trunc
                 info = {"_final_obs": done}
-                if done.any():      # rare: second, blocking D2H of the terminal observations
-                    self._h_final.copy_(self._final_obs)
-                    info["final_obs"] = self._h_final.numpy().reshape(self._E, self._D, self._obs_dim).copy()
+                if done.any():
+                    # rare rows only: gather the finished aviaries' terminal observations on the device, one small D2H
+                    idx = np.flatnonzero(done)
+                    idx_dev = torch.from_numpy(idx).to(self.device, non_blocking=True)
+                    rows = torch.index_select(self._final_view, 0, idx_dev).cpu()
+                    info["final_obs"] = rows.numpy()          # [k, D, obs_dim], k = number of finished aviaries
+                    info["final_obs_env"] = idx                # their indices
             return o, rew, term, trunc, info
 
     def _single_result(self, obs):
