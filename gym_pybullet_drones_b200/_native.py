@@ -23,6 +23,7 @@ TASK_NONE, TASK_HOVER = 0, 1
 EFFECT_GND, EFFECT_DRAG, EFFECT_DW = 1, 2, 4
 FLAG_AUTORESET_SAME_STEP, FLAG_AUTORESET_NEXT_STEP, FLAG_RPY_F32 = 1, 2, 4
 FLAG_AUTORESET_CLEARS_PID, FLAG_AUTORESET_CLEARS_HISTORY = 8, 16
+FLAG_OBS_STATE20 = 32
 FLAG_SKIP_EPILOGUE, FLAG_RPM_FROM_LAST = 0x100, 0x200
 ABI_VERSION = 1
 

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
         if (a.flags & QS_FLAG_RPM_FROM_LAST) {
             rpm[0] = rpm_prev[0]; rpm[1] = rpm_prev[1]; rpm[2] = rpm_prev[2]; rpm[3] = rpm_prev[3];
         } else {
-            qs::decode_action<PIDACT>(P, RAW ? (int)QS_ACT_RAW_RPM : a.act_type, act, d, cur_yaw, pst, rpm);
+            qs::decode_action<PIDACT>(P, a.act_type, act, d, cur_yaw, pst, rpm);
         }
     }
 
@@ -511,9 +511,11 @@ __global__ void __launch_bounds__(128) pid_kernel(const __grid_constant__ PidArg
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Pairwise downwash for large aviaries: classic tiled all-pairs.  Block = 256 drones of ONE aviary; the
-// aviary's positions stream through shared memory in tiles of 256.  The pair term is evaluated in float32
-// (predicate first, expf only for pairs in range), the sum is accumulated in float64.
+// Pairwise downwash for large aviaries: tiled all-pairs.  A CTA owns 128 drones of ONE aviary and runs 1024 threads:
+// thread (slice s, drone n) evaluates the tile entries k = s (mod 8), so a 16 384-drone formation fills 128 SMs with
+// 32 warps each instead of 64 SMs with 8.  The aviary's positions stream through shared memory in tiles of 256; the
+// pair term is float32 (predicate first, expf only for pairs in range), partial sums are float64 and are combined in a
+// fixed order through shared memory (deterministic).
 // ---------------------------------------------------------------------------------------------------------
 struct DwArgs {
     float prop_radius, dw1, dw2, dw3;
@@ -523,24 +525,29 @@ struct DwArgs {
     long long N;
 };
 
-__global__ void __launch_bounds__(256) downwash_kernel(const __grid_constant__ DwArgs a) {
-    __shared__ float4 tile[256];
+constexpr int kDwDrones = 128, kDwSlices = 8, kDwTile = 256;
+
+__global__ void __launch_bounds__(kDwDrones * kDwSlices) downwash_kernel(const __grid_constant__ DwArgs a) {
+    __shared__ float4 tile[kDwTile];
+    __shared__ double part[kDwSlices][kDwDrones];
     const int env = blockIdx.x / a.tiles_per_env;
     const int tb = blockIdx.x - env * a.tiles_per_env;
     const long long base = (long long)env * a.D;
-    const int n = tb * 256 + threadIdx.x;                 // my drone inside the aviary
+    const int ln = threadIdx.x % kDwDrones, sl = threadIdx.x / kDwDrones;
+    const int n = tb * kDwDrones + ln;                    // my drone inside the aviary
     const bool live = n < a.D;
-    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 me = make_float4(0.f, 0.f, 3e30f, 0.f);
     if (live) me = ldg4(a.planes, base + n);
     double acc = 0.0;
-    for (int j0 = 0; j0 < a.D; j0 += 256) {
-        const int j = j0 + threadIdx.x;
-        tile[threadIdx.x] = (j < a.D) ? ldg4(a.planes, base + j) : make_float4(0.f, 0.f, -1e30f, 0.f);
+    for (int j0 = 0; j0 < a.D; j0 += kDwTile) {
+        if (threadIdx.x < kDwTile) {
+            const int j = j0 + threadIdx.x;
+            tile[threadIdx.x] = (j < a.D) ? ldg4(a.planes, base + j) : make_float4(0.f, 0.f, -3e30f, 0.f);
+        }
         __syncthreads();
-        const int cnt = min(256, a.D - j0);
-        float part = 0.f;
+        float part_f = 0.f;
 #pragma unroll 8
-        for (int k = 0; k < cnt; ++k) {
+        for (int k = sl; k < kDwTile; k += kDwSlices) {
             const float4 o = tile[k];
             const float dz = o.z - me.z;
             const float dx = o.x - me.x, dy = o.y - me.y;
@@ -550,13 +557,20 @@ __global__ void __launch_bounds__(256) downwash_kernel(const __grid_constant__ D
                 const float alpha = a.dw1 * (rr * rr);
                 const float beta = a.dw2 * dz + a.dw3;
                 const float u2 = dxy2 / (beta * beta);
-                part -= alpha * expf(-0.5f * u2);
+                part_f -= alpha * expf(-0.5f * u2);
             }
         }
-        acc += (double)part;
+        acc += (double)part_f;
         __syncthreads();
     }
-    if (live) a.fz[base + n] = (float)acc;
+    part[sl][ln] = acc;
+    __syncthreads();
+    if (sl == 0 && live) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < kDwSlices; ++k) t += part[k][ln];
+        a.fz[base + n] = (float)t;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -674,7 +688,9 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
     if (int rc = check_state(st, autoreset ? 1 : 0)) return rc;
     if (n_envs <= 0 || drones_per_env <= 0 || substeps <= 0) return fail(QS_ERR_SIZE, "qs_step: n_envs, drones_per_env, substeps must be > 0");
     const int A = act_width(act_type);
-    if (A < 0 || act_type == QS_ACT_RAW_RPM) return fail(QS_ERR_ENUM, "qs_step: bad act_type (use qs_dyn_substeps for raw rpm)");
+    const bool state20 = flags & QS_FLAG_OBS_STATE20;
+    if (A < 0 || (act_type == QS_ACT_RAW_RPM && !state20)) return fail(QS_ERR_ENUM, "qs_step: bad act_type (use qs_dyn_substeps for raw rpm)");
+    if (state20 && (task != QS_TASK_NONE || autoreset)) return fail(QS_ERR_UNSUPPORTED, "qs_step: OBS_STATE20 needs QS_TASK_NONE and no autoreset");
     if (task != QS_TASK_NONE && task != QS_TASK_HOVER) return fail(QS_ERR_ENUM, "qs_step: bad task");
     if (effects & ~7u) return fail(QS_ERR_ENUM, "qs_step: bad effects");
     if ((flags & QS_FLAG_AUTORESET_SAME_STEP) && (flags & QS_FLAG_AUTORESET_NEXT_STEP)) return fail(QS_ERR_ENUM, "qs_step: two autoreset modes");
@@ -682,9 +698,9 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
     if (A == 4 && !aligned16(io->action)) return fail(QS_ERR_ALIGN, "qs_step: [N][4] action must be 16-byte aligned");
     const bool skip = flags & QS_FLAG_SKIP_EPILOGUE;
     if ((flags & QS_FLAG_RPM_FROM_LAST) && !st->last_rpm) return fail(QS_ERR_NULL, "qs_step: RPM_FROM_LAST needs QsState.last_rpm");
-    if (!skip && (!io->reward || !io->terminated || !io->truncated)) return fail(QS_ERR_NULL, "qs_step: reward/terminated/truncated is NULL");
+    if (!skip && !state20 && (!io->reward || !io->terminated || !io->truncated)) return fail(QS_ERR_NULL, "qs_step: reward/terminated/truncated is NULL");
     if (io->act_buffer_size < 0) return fail(QS_ERR_SIZE, "qs_step: act_buffer_size < 0");
-    if (io->obs && io->act_buffer_size > 0 && !io->obs_prev) return fail(QS_ERR_NULL, "qs_step: obs_prev is NULL");
+    if (io->obs && io->act_buffer_size > 0 && !state20 && !io->obs_prev) return fail(QS_ERR_NULL, "qs_step: obs_prev is NULL");
     if (io->obs && io->obs == io->obs_prev) return fail(QS_ERR_UNSUPPORTED, "qs_step: obs and obs_prev must be distinct buffers");
     if (task == QS_TASK_HOVER && !st->target_pos) return fail(QS_ERR_NULL, "qs_step: target_pos is NULL");
     if (task == QS_TASK_HOVER && !aligned16(st->target_pos)) return fail(QS_ERR_ALIGN, "qs_step: target_pos must be 16-byte aligned");
@@ -700,7 +716,7 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
     memset(&a, 0, sizeof(a));
     a.P = *p; a.st = *st; a.io = *io;
     a.act_type = act_type; a.task = task; a.n_envs = n_envs; a.D = drones_per_env; a.substeps = substeps;
-    a.N = n_envs * drones_per_env; a.A = A; a.obs_dim = 12 + io->act_buffer_size * A;
+    a.N = n_envs * drones_per_env; a.A = A; a.obs_dim = state20 ? 20 : 12 + io->act_buffer_size * A;
     a.tpb = block_size_for(drones_per_env);
     a.counter_inc = io->tick_substeps > 0 ? io->tick_substeps : substeps;
     a.effects = effects; a.flags = flags;
@@ -710,7 +726,11 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
         const size_t row_bytes = (size_t)a.obs_dim * 4, span = row_bytes * a.tpb;
         const bool aligned = aligned16(io->obs_prev) && aligned16(io->obs) && (span % 16 == 0) && ((row_bytes * ((size_t)a.N % a.tpb)) % 16 == 0);
         a.stage_rows = 0;
-        if (io->obs && io->act_buffer_size > 0 && span <= kStageLimit) a.stage_rows = (aligned && A == 4) ? 1 : 2;
+        if (io->obs && io->act_buffer_size > 0 && !state20 && span <= kStageLimit) a.stage_rows = (aligned && A == 4) ? 1 : 2;
+    }
+    if (state20) {
+        const cudaError_t e2 = pid_act ? launch_step<true, true>(a, (cudaStream_t)stream) : launch_step<true, false>(a, (cudaStream_t)stream);
+        return e2 == cudaSuccess ? 0 : cuda_fail(e2, "qs_step launch");
     }
     const cudaError_t e = pid_act ? launch_step<false, true>(a, (cudaStream_t)stream) : launch_step<false, false>(a, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_step launch");
@@ -765,9 +785,9 @@ int qs_downwash(const QsParams* p, const QsState* st, int n_envs, int drones_per
     if (n_envs <= 0 || drones_per_env <= 0) return fail(QS_ERR_SIZE, "qs_downwash: sizes must be > 0");
     DwArgs a;
     a.prop_radius = (float)p->prop_radius; a.dw1 = (float)p->dw_coeff[0]; a.dw2 = (float)p->dw_coeff[1]; a.dw3 = (float)p->dw_coeff[2];
-    a.planes = st->planes; a.fz = fz_out; a.D = drones_per_env; a.tiles_per_env = (drones_per_env + 255) / 256;
+    a.planes = st->planes; a.fz = fz_out; a.D = drones_per_env; a.tiles_per_env = (drones_per_env + kDwDrones - 1) / kDwDrones;
     a.N = (long long)n_envs * drones_per_env;
-    downwash_kernel<<<n_envs * a.tiles_per_env, 256, 0, (cudaStream_t)stream>>>(a);
+    downwash_kernel<<<n_envs * a.tiles_per_env, kDwDrones * kDwSlices, 0, (cudaStream_t)stream>>>(a);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_downwash launch");
 }

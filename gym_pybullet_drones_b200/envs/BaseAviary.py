@@ -173,6 +173,10 @@ class BaseAviary(Env):
         """dict(xy_bound=..., episode_len_sec=...) overrides for QsParams."""
         return {}
 
+    def _state20_obs(self):
+        """True: observations are the [D, 20] state vectors of _getDroneStateVector (CtrlAviary, VelocityAviary)."""
+        return self._act_type() == N.ACT_RAW_RPM
+
     def _target_table(self):
         """[D,3] / [E,D,3] TARGET_POS or None."""
         return None
@@ -203,8 +207,10 @@ class BaseAviary(Env):
         dev, E, D, n = self.device, self._E, self._D, self._N
         self._A = self._act_width()
         self._B = self._act_buffer_size()
-        raw = self._act_type() == N.ACT_RAW_RPM
+        raw = self._state20_obs()
         self._obs_dim = 20 if raw else 12 + self._B * self._A
+        if raw and self._act_type() != N.ACT_RAW_RPM:
+            self._flags |= N.FLAG_OBS_STATE20
         f32 = dict(dtype=torch.float32, device=dev)
         self._planes = torch.zeros((4, n, 4), **f32)
         self._last_rpm = torch.zeros((n, 4), **f32)
@@ -253,7 +259,7 @@ class BaseAviary(Env):
         self._obs_ptr = [b.data_ptr() for b in self._obs_buf]
         self._obs_view = [b.view(E, D, self._obs_dim) for b in self._obs_buf]
         self._final_view = self._final_obs.view(E, D, self._obs_dim) if self._final_obs is not None else None
-        self._simple_launch = self._dw_fz is None and not raw
+        self._simple_launch = self._dw_fz is None and not raw and not self._state20_obs()
         self._qs_step = self._lib.qs_step
         self._step_head = (C.byref(self._P), C.byref(self._st), C.byref(io), self._act_type(), self._task(),
                            E, D, self.PYB_STEPS_PER_CTRL, self._effects, self._flags)
@@ -331,7 +337,7 @@ class BaseAviary(Env):
     def _housekeeping(self, mask=None):
         """BaseAviary._housekeeping (BaseAviary.py:451-505): counters, poses, velocities, rates, last action."""
         with self._on_device():
-            raw = self._act_type() == N.ACT_RAW_RPM
+            raw = self._state20_obs()
             m = None if mask is None else mask.data_ptr()
             rc = self._lib.qs_reset(C.byref(self._P), C.byref(self._st), m, self._E, self._D, 0,
                                     self._obs_buf[self._cur].data_ptr(), self._obs_dim, 1 if raw else 0, self._stream())
@@ -378,6 +384,8 @@ class BaseAviary(Env):
         stream = self._stream()
         raw = self._act_type() == N.ACT_RAW_RPM
         L = self._lib
+        if self._state20_obs():
+            self._reward.fill_(-1.0)                       # dummy task (CtrlAviary.py:144-185, VelocityAviary.py:172-228)
         if self._dw_fz is None:
             if raw:
                 rc = L.qs_dyn_substeps(C.byref(self._P), C.byref(self._st), io.action, io.obs, None,

@@ -60,6 +60,8 @@ enum { QS_FLAG_AUTORESET_SAME_STEP = 1,   /* SB3 VecEnv semantics: done envs are
           (SURVEY.md 3.3); autoreset keeps that behaviour unless asked otherwise: */
        QS_FLAG_AUTORESET_CLEARS_PID = 8,
        QS_FLAG_AUTORESET_CLEARS_HISTORY = 16,
+       QS_FLAG_OBS_STATE20 = 32,          /* qs_step writes [N][20] _getDroneStateVector rows instead of KIN observations (no action
+                                             buffer, task must be QS_TASK_NONE): VelocityAviary = act VEL + this flag */
        /* Split-substep protocol for aviaries larger than one CTA with downwash (positions couple the drones
           every substep, so each substep is its own launch: qs_downwash, then qs_step(substeps=1)):
           all but the last launch of a tick pass SKIP_EPILOGUE (no obs/reward/flags/counter); all but the first

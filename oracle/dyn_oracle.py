@@ -349,7 +349,7 @@ class OracleAviary:
     def __init__(self, kind="hover", num_envs=1, num_drones=1, drone_model="cf2x", pyb_freq=240, ctrl_freq=None,
                  act="rpm", initial_xyzs=None, initial_rpys=None, effects=0, dtype=np.float64):
         if ctrl_freq is None:
-            ctrl_freq = 240 if kind == "ctrl" else 30                  # CtrlAviary.py:19-20, HoverAviary.py:16-17
+            ctrl_freq = 240 if kind in ("ctrl", "velocity") else 30    # CtrlAviary.py:19-20, VelocityAviary.py:22-23, HoverAviary.py:16-17
         if kind == "hover":
             num_drones = 1                                             # HoverAviary.py:54
         self.kind, self.E, self.D, self.dtype = kind, num_envs, num_drones, dtype
@@ -369,7 +369,12 @@ class OracleAviary:
             off = np.array([[0, 0, 1 / (i + 1)] for i in range(num_drones)])
             self.TARGET_POS = (self.INIT_XYZS + off).astype(dtype)     # MultiHoverAviary.py:71
             self.xy_bound = 2.0
-        if kind != "ctrl":
+        if kind == "velocity":                                         # VelocityAviary.py:59-78
+            self.act, self.A, self.B = "vel", 4, 0
+            self.action_buffer = []
+            self.ctrl = OraclePID(self.E * self.D, "cf2x", dtype=dtype)
+            self.SPEED_LIMIT = 0.03 * P.MAX_SPEED_KMH * (1000 / 3600)
+        elif kind != "ctrl":
             self.A = _ACT_WIDTH[act]
             self.B = int(ctrl_freq // 2)                               # BaseRLAviary.py:66
             self.action_buffer = [np.zeros((self.E, self.D, self.A), dtype) for _ in range(self.B)]   # :153-154
@@ -408,8 +413,9 @@ class OracleAviary:
         action = np.asarray(action)
         if self.kind == "ctrl":
             return np.clip(action.astype(self.dtype), 0, P.MAX_RPM)
-        self.action_buffer.pop(0)
-        self.action_buffer.append(action.copy())                                 # :187 (deque maxlen)
+        if self.kind != "velocity":
+            self.action_buffer.pop(0)
+            self.action_buffer.append(action.copy())                             # :187 (deque maxlen)
         # NumPy-2 promotion (reference pins numpy ^2.2, pyproject.toml:15): python scalars are weak,
         # so with float32 actions `1+0.05*target` is evaluated in float32 and only the product with
         # the np.float64 HOVER_RPM is float64; the VEL target velocity is float32 end to end.
@@ -440,7 +446,7 @@ class OracleAviary:
         return rpm.reshape(self.E, self.D, 4)
 
     def _obs(self):
-        if self.kind == "ctrl":                                                  # CtrlAviary.py:106-117
+        if self.kind in ("ctrl", "velocity"):                                    # CtrlAviary.py:106-117, VelocityAviary.py:111-125
             return self.state_vector()
         kin = np.concatenate([self.pos, self.rpy, self.vel, self.ang_v], axis=-1).astype(np.float32)   # BaseRLAviary.py:310-315
         return np.concatenate([kin] + [b.astype(np.float32) for b in self.action_buffer], axis=-1)    # :317-318
@@ -464,7 +470,7 @@ class OracleAviary:
             self.last_clipped_action = rpm                                       # :372
         self.rpy = quat_to_euler(self.quat)                                      # :374
         obs = self._obs()                                                        # :376
-        if self.kind == "ctrl":
+        if self.kind in ("ctrl", "velocity"):
             reward = -np.ones(self.E); term = np.zeros(self.E, bool); trunc = np.zeros(self.E, bool)
         else:
             e = np.linalg.norm(self.TARGET_POS - self.pos, axis=-1)              # [E, D]

@@ -221,6 +221,17 @@ def main():
         out.update(flat(dm.value, rec))
     save("ctrl_models_300", **out)
 
+    # ---- VelocityAviary (examples/pid_velocity.py shape): 2 drones, 240/240 Hz, piecewise-constant velocity commands ----
+    with quiet():
+        env = R.VelocityAviary(num_drones=2, physics=DYN, pyb_freq=240, ctrl_freq=240)
+    rng = np.random.default_rng(44)
+    seg = rng.uniform(-1, 1, (5, 2, 4)).astype(np.float32)
+    seg[..., 3] = np.abs(seg[..., 3])
+    seg[2, 1, 0:3] = 0                                   # zero direction -> zero unit vector branch (VelocityAviary.py:150-153)
+    acts = np.repeat(seg, 96, axis=0)
+    rec = run_env(env, acts, record_obs_every=1)
+    save("velocity_aviary_480", **rec)
+
     # ---- formula-level pins for the PYB-only aerodynamic models ---------------------------------
     rng = np.random.default_rng(5)
     out = {}

@@ -1,0 +1,110 @@
+"""API conformance on the GPU: the surface examples/learn.py, pid.py and SB3 touch."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sb3_vecenv_protocol_episode_stats():
+    """SB3 VecEnv protocol (what make_vec_env + Monitor give learn.py): zero action -> every episode is the reference's
+    KAT episode: 242 steps, return 333.8626, time-limit truncation, terminal observation = last obs of the episode."""
+    from gym_pybullet_drones_b200.envs import HoverAviary
+    from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
+    from gym_pybullet_drones_b200.vec import SB3VecAviary
+    E = 16
+    venv = SB3VecAviary(HoverAviary, E, physics=Physics.DYN, act=ActionType.ONE_D_RPM)
+    assert venv.num_envs == E and venv.observation_space.shape == (1, 27) and venv.action_space.shape == (1, 1)
+    obs = venv.reset()
+    assert obs.shape == (E, 1, 27) and obs.dtype == np.float32
+    act = np.zeros((E, 1, 1), np.float32)
+    last = None
+    for t in range(242):
+        last = obs
+        venv.step_async(act)
+        obs, rews, dones, infos = venv.step_wait()
+        assert obs.shape == (E, 1, 27) and rews.shape == (E,) and dones.shape == (E,) and len(infos) == E
+        if t < 241:
+            assert not dones.any() and infos[0] == {}
+    assert dones.all()
+    for i in range(E):
+        ep = infos[i]["episode"]
+        assert ep["l"] == 242 and abs(ep["r"] - 333.862626904298) < 1e-2
+        assert infos[i]["TimeLimit.truncated"] is True
+        term_obs = infos[i]["terminal_observation"]
+        assert term_obs.shape == (1, 27) and abs(term_obs[0, 2] - 0.1125) < 1e-6
+    # after the auto-reset the returned obs is the reset observation and the counters restarted
+    assert np.allclose(obs[:, 0, :3], [0, 0, 0.1125]) and int(venv.env.step_counter.max()) == 0
+    assert venv.env_is_wrapped(type("Monitor", (), {})) == [True] * E
+    assert venv.get_attr("CTRL_FREQ") == [30] * E
+    venv.close()
+
+
+def test_reference_attribute_surface():
+    """Attributes and methods learn.py / pid.py read (learn.py:143,157,168,189; pid.py:116,132,142)."""
+    from gym_pybullet_drones_b200.envs import CtrlAviary, HoverAviary, MultiHoverAviary
+    from gym_pybullet_drones_b200.utils.enums import ActionType, DroneModel, ObservationType, Physics
+    env = MultiHoverAviary(num_drones=2, obs=ObservationType.KIN, act=ActionType.ONE_D_RPM)      # learn.py's call
+    assert env.NUM_DRONES == 2 and env.CTRL_FREQ == 30 and env.PYB_FREQ == 240 and env.EPISODE_LEN_SEC == 8
+    assert abs(env.CTRL_TIMESTEP - 1 / 30) < 1e-15 and env.PYB_STEPS_PER_CTRL == 8 and env.ACTION_BUFFER_SIZE == 15
+    assert env.action_space.shape == (2, 1) and env.observation_space.shape == (2, 27)
+    assert env.action_space.dtype == np.float32 and env.observation_space.dtype == np.float32
+    assert np.allclose(env.INIT_XYZS, [[0, 0, 0.1125], [0.1588, 0.1588, 0.1125]])
+    assert np.allclose(env.TARGET_POS, [[0, 0, 1.1125], [0.1588, 0.1588, 0.6125]])
+    assert abs(env.HOVER_RPM - 14468.429183500699) < 1e-9 and abs(env.MAX_RPM - 21702.64377525105) < 1e-9
+    obs, info = env.reset(seed=42, options={})
+    assert obs.shape == (2, 27) and info == {"answer": 42}
+    obs, r, te, tr, info = env.step(env.action_space.sample())
+    assert obs.shape == (2, 27) and isinstance(r, float) and isinstance(te, bool) and isinstance(tr, bool)
+    env.render()
+    env.close()
+    assert env.getPyBulletClient() == -1 and list(env.getDroneIds()) == [0, 1]
+    c = CtrlAviary(drone_model=DroneModel.CF2X, num_drones=3, physics=Physics.PYB, neighbourhood_radius=10, pyb_freq=240, ctrl_freq=48)
+    assert c.action_space.shape == (3, 4) and c.observation_space.shape == (3, 20) and abs(c.action_space.high[0, 0] - c.MAX_RPM) < 1e-2
+    obs, _ = c.reset()
+    assert obs.shape == (3, 20) and c._getAdjacencyMatrix().shape == (3, 3)
+    assert c._getDroneStateVector(1).shape == (20,)
+    with pytest.raises(ValueError):
+        HoverAviary(pyb_freq=240, ctrl_freq=7)                       # BaseAviary.py:79-80
+    with pytest.raises(NotImplementedError):
+        HoverAviary(obs=ObservationType.RGB)
+    with pytest.raises(ValueError):
+        CtrlAviary(num_drones=2, initial_xyzs=np.zeros((3, 3)))
+
+
+def test_policy_rollout_on_device_config3_shape():
+    """Config 3 shape at test size: an SB3-MlpPolicy-shaped torch network drives the vectorised env entirely on the
+    device (no host copies), SAME_STEP autoreset, under a CUDA graph."""
+    from gym_pybullet_drones_b200.envs import MultiHoverAviary
+    from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
+    E, D = 4096, 2
+    env = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E, autoreset="same_step")
+    torch.manual_seed(0)
+    pi = torch.nn.Sequential(torch.nn.Linear(D * 72, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(),
+                             torch.nn.Linear(64, D * 4)).cuda()
+    obs, _ = env.reset()
+    act = torch.zeros((E, D, 4), device="cuda")
+    ret = torch.zeros(E, device="cuda")
+    n_done = torch.zeros((), device="cuda")
+
+    def one_step(o):
+        with torch.no_grad():
+            mean = pi(o.reshape(E, -1))
+            act.copy_((mean + 0.3 * torch.randn_like(mean)).clamp(-1, 1).view(E, D, 4))
+        o2, rew, term, trunc, info = env.step(act)
+        ret.add_(rew)
+        n_done.add_(info["_final_obs"].sum())
+        return o2
+    for _ in range(4):
+        obs = one_step(obs)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    static_obs = [env._obs_view[0], env._obs_view[1]]
+    with torch.cuda.graph(g):
+        one_step(static_obs[env._cur])
+        one_step(static_obs[env._cur])
+    for _ in range(60):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.isfinite(ret).all() and float(ret.mean()) > 0 and float(n_done) > 0
+    assert int(env.step_counter.max()) <= 8 * 124

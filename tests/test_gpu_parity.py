@@ -214,6 +214,24 @@ def test_pid_circle_workload(golden):
         action = rpm
 
 
+def test_velocity_aviary_golden(golden):
+    """VelocityAviary: act VEL through the embedded PID, 20-float state vectors out, 240/240 Hz."""
+    from gym_pybullet_drones_b200.envs import VelocityAviary
+    from gym_pybullet_drones_b200.utils.enums import Physics
+    g = golden("velocity_aviary_480")
+    env = VelocityAviary(num_drones=2, physics=Physics.DYN, pyb_freq=240, ctrl_freq=240)
+    assert env.action_space.shape == (2, 4) and env.observation_space.shape == (2, 20) and abs(env.SPEED_LIMIT - 0.25) < 1e-12
+    obs, _ = env.reset()
+    assert relerr(obs, g["obs0"]) < 1e-6
+    acts = g["actions"]
+    for t in range(acts.shape[0]):
+        obs, r, te, tr, _ = env.step(acts[t])
+        ref = g["obs"][t]
+        assert r == -1 and te is False and tr is False
+        assert relerr(obs[:, 0:3], ref[:, 0:3]) < 2e-5 and quat_err(obs[:, 3:7], ref[:, 3:7]) < 2e-5, t
+        assert relerr(obs[:, 7:16], ref[:, 7:16]) < 1e-4 and relerr(obs[:, 16:20], ref[:, 16:20]) < 1e-4, t
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # (b) seeded inputs against the float64 oracle
 # ---------------------------------------------------------------------------------------------------------------
@@ -390,19 +408,28 @@ def test_autoreset_next_step_semantics():
 
 
 def test_numpy_vector_api_roundtrip_equals_tensor_api():
+    """NumPy in / NumPy out (pinned staging, compact final_obs rows) returns exactly what the tensor API returns."""
     _, _, _, MultiHoverAviary, ActionType, _, Physics, _ = _imports()
     E, D = 128, 2
     rng = np.random.default_rng(3)
-    e1 = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E)
-    e2 = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E)
+    kw = dict(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E, autoreset="same_step")
+    e1, e2 = MultiHoverAviary(**kw), MultiHoverAviary(**kw)
     o1, _ = e1.reset(); o2, _ = e2.reset()
-    for t in range(20):
+    seen = 0
+    for t in range(120):
         a = rng.uniform(-1, 1, (E, D, 4)).astype(np.float32)
-        o1, r1, te1, tr1, _ = e1.step(torch.from_numpy(a).cuda())
-        o2, r2, te2, tr2, _ = e2.step(a)
+        o1, r1, te1, tr1, i1 = e1.step(torch.from_numpy(a).cuda())
+        o2, r2, te2, tr2, i2 = e2.step(a)
         assert isinstance(o2, np.ndarray) and o2.dtype == np.float32 and r2.shape == (E,) and te2.dtype == bool
         assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(te1.cpu().numpy(), te2) and np.array_equal(tr1.cpu().numpy(), tr2)
+        done = te2 | tr2
+        assert np.array_equal(i1["_final_obs"].cpu().numpy(), done) and np.array_equal(i2["_final_obs"], done)
+        if done.any():
+            seen += int(done.sum())
+            assert np.array_equal(i2["final_obs_env"], np.flatnonzero(done))
+            assert np.array_equal(i2["final_obs"], i1["final_obs"].cpu().numpy()[done])
+    assert seen > 20
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -175,6 +175,18 @@ def test_ctrl_other_models(golden, model):
         assert relerr(env.rpy_rates[0], g[model + "_rpy_rates"][t]) < 1e-9
 
 
+def test_velocity_aviary(golden):
+    g = golden("velocity_aviary_480")
+    env = O.OracleAviary("velocity", 1, 2)
+    acts = g["actions"]
+    o0 = env.reset()
+    assert relerr(o0[0], g["obs0"]) < 1e-12
+    for t in range(acts.shape[0]):
+        obs, r, te, tr = env.step(acts[t][None])
+        assert relerr(obs[0], g["obs"][t]) < 1e-9, t
+        assert r[0] == -1 and not te[0] and not tr[0]
+
+
 @pytest.mark.parametrize("model", ["cf2x", "cf2p"])
 def test_effect_formulas(golden, model):
     """_groundEffect/_drag/_downwash exist only on the reference's PYB_* branches: pinned at force level."""

@@ -1,0 +1,100 @@
+"""Throughput of the other BASELINE.json configs (not the headline bench line): writes gpurun_out/configs_r01.json.
+    config 2: 4096 x HoverAviary with the embedded DSLPIDControl (act=PID), + stand-alone qs_pid_control
+    config 3b: learn.py's ONE_D_RPM variant of the headline workload (A=1, obs 27)
+    config 4: one 16384-drone formation with ground effect + downwash (pairwise kernel + one launch per substep)
+    S=1:      65536 drones at 240 Hz control (B=120 -> obs 492 floats, 4006 algorithmic bytes per drone-step)
+"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from gym_pybullet_drones_b200.control import DSLPIDControl
+from gym_pybullet_drones_b200.envs import CtrlAviary, HoverAviary, MultiHoverAviary
+from gym_pybullet_drones_b200.utils.enums import ActionType, DroneModel, Physics
+
+PEAK = 6572.5
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, n, warm=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+out = {}
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(0)
+
+# config 2: several independent 4096-env batches rotated (a single 4096 batch is 2.4 MB: launch-latency bound, L2 resident)
+E = 4096
+envs = [HoverAviary(physics=Physics.DYN, act=ActionType.PID, num_envs=E, autoreset="same_step") for _ in range(8)]
+sp = [(torch.tensor([-0.5, -0.5, 0.5], device=dev) + torch.rand((E, 1, 3), device=dev, generator=g)) for _ in range(8)]
+for e in envs:
+    e.reset()
+k = [0]
+def f2():
+    i = k[0] % 8; k[0] += 1
+    envs[i].step(sp[i])
+ms = timed(f2, 2000, 50)
+out["config2_hover_pid_4096"] = {"drones": E, "S": 8, "ms_per_step": ms, "drone_steps_per_s": E / (ms * 1e-3), "alg_bytes": 598,
+                                  "hbm_frac": 598 * E / (ms * 1e-3) / 1e9 / PEAK, "note": "4096 drones = 2.4 MB per launch: launch-latency bound"}
+for n in (4096, 1048576):
+    ctrl = DSLPIDControl(DroneModel.CF2X, num_drones=n)
+    pos = torch.rand((n, 3), device=dev, generator=g); vel = torch.rand((n, 3), device=dev, generator=g) - 0.5
+    q = torch.randn((n, 4), device=dev, generator=g); q = q / q.norm(dim=1, keepdim=True)
+    tp = torch.rand((n, 3), device=dev, generator=g)
+    ms = timed(lambda: ctrl.computeControl(1 / 48, pos, q, vel, None, tp), 200, 10)
+    out["qs_pid_control_%d" % n] = {"n": n, "ms_per_call": ms, "calls_per_s": n / (ms * 1e-3), "alg_bytes": 192, "hbm_frac": 192 * n / (ms * 1e-3) / 1e9 / PEAK}
+
+# config 3b: ONE_D_RPM
+E, D = 32768, 2
+envs = [MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.ONE_D_RPM, num_envs=E, autoreset="same_step") for _ in range(8)]
+acts = [torch.rand((E, D, 1), device=dev, generator=g) * 2 - 1 for _ in range(8)]
+for e in envs:
+    e.reset()
+k = [0]
+def f3():
+    i = k[0] % 8; k[0] += 1
+    envs[i].step(acts[i])
+ms = timed(f3, 2000, 50)
+out["config3_multihover_one_d_rpm_65536"] = {"drones": E * D, "S": 8, "ms_per_step": ms, "drone_steps_per_s": E * D / (ms * 1e-3), "alg_bytes": 286,
+                                             "hbm_frac": 286 * E * D / (ms * 1e-3) / 1e9 / PEAK}
+del envs
+
+# S=1: 240 Hz control, B=120
+E, D = 32768, 2
+env = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, pyb_freq=240, ctrl_freq=240, num_envs=E, autoreset="same_step")
+a = torch.rand((E, D, 4), device=dev, generator=g) * 2 - 1
+env.reset()
+ms = timed(lambda: env.step(a), 500, 20)
+out["rpm_240hz_S1_65536"] = {"drones": E * D, "S": 1, "obs_dim": 492, "ms_per_step": ms, "drone_steps_per_s": E * D / (ms * 1e-3), "alg_bytes": 4006,
+                             "hbm_frac": 4006 * E * D / (ms * 1e-3) / 1e9 / PEAK, "note": "working set 258 MB > L2; unstaged writer (span too large for shared memory)"}
+del env
+
+# config 4: one aviary of 16384 drones, 128x128 grid 0.15 m pitch, z = 0.1 + 0.05*(i mod 16), GND|DW
+Dn = 16384
+i = np.arange(Dn)
+xyz = np.stack([0.15 * (i % 128), 0.15 * (i // 128), 0.1 + 0.05 * (i % 16)], axis=1)
+env = CtrlAviary(num_drones=Dn, initial_xyzs=xyz, physics=Physics.PYB_GND_DRAG_DW, pyb_freq=240, ctrl_freq=240, num_envs=1)
+env.reset()
+rpm = torch.full((1, Dn, 4), float(env.HOVER_RPM), device=dev)
+ms = timed(lambda: env.step(rpm), 50, 5)
+import ctypes as C
+from gym_pybullet_drones_b200 import _native as N
+fz = torch.zeros(Dn, device=dev)
+msdw = timed(lambda: N.lib().qs_downwash(C.byref(env._P), C.byref(env._st), 1, Dn, fz.data_ptr(), torch.cuda.current_stream().cuda_stream), 50, 5)
+out["config4_formation_16384_gnd_drag_dw"] = {"drones": Dn, "S": 1, "ms_per_step": ms, "drone_steps_per_s": Dn / (ms * 1e-3),
+                                              "downwash_kernel_ms": msdw, "pairs_per_s": Dn * Dn / (msdw * 1e-3),
+                                              "note": "pairwise term is FP32 ALU/SFU bound (N^2 = 2.7e8 pairs per substep), not HBM bound"}
+json.dump(out, open("gpurun_out/configs_r01.json", "w"), indent=1)
+print(json.dumps(out, indent=1))
