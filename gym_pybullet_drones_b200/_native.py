@@ -64,8 +64,17 @@ class QsStepIO(C.Structure):
     ]
 
 
+class QsRolloutIO(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p), ("actions_out", C.c_void_p), ("obs_init", C.c_void_p), ("obs", C.c_void_p), ("obs_last", C.c_void_p),
+        ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("done", C.c_void_p),
+        ("seed", C.c_ulonglong), ("tick0", C.c_longlong), ("T", C.c_int), ("act_buffer_size", C.c_int),
+    ]
+
+
 EXPORTS = ["qs_abi_version", "qs_last_error", "qs_sizeof_params", "qs_sizeof_state", "qs_sizeof_step_io",
-           "qs_step", "qs_dyn_substeps", "qs_pid_control", "qs_downwash", "qs_reset"]
+           "qs_sizeof_rollout_io", "qs_step", "qs_rollout", "qs_rollout_max_ticks", "qs_dyn_substeps", "qs_pid_control",
+           "qs_downwash", "qs_reset"]
 
 
 def build(force=False, verbose=False):
@@ -99,11 +108,16 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.qs_abi_version.restype = C.c_int
     L.qs_last_error.restype = C.c_char_p
-    for n in ("qs_sizeof_params", "qs_sizeof_state", "qs_sizeof_step_io"):
+    for n in ("qs_sizeof_params", "qs_sizeof_state", "qs_sizeof_step_io", "qs_sizeof_rollout_io"):
         getattr(L, n).restype = C.c_int
     L.qs_step.restype = C.c_int
     L.qs_step.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.POINTER(QsStepIO), C.c_int, C.c_int,
                           C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
+    L.qs_rollout.restype = C.c_int
+    L.qs_rollout.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.POINTER(QsRolloutIO), C.c_int, C.c_int,
+                             C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
+    L.qs_rollout_max_ticks.restype = C.c_int
+    L.qs_rollout_max_ticks.argtypes = [C.c_int, C.c_int, C.c_int]
     L.qs_dyn_substeps.restype = C.c_int
     L.qs_dyn_substeps.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
@@ -119,7 +133,8 @@ def lib():
                            C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     if L.qs_abi_version() != ABI_VERSION:
         raise ImportError("libquadsim.so ABI %d != binding ABI %d: rebuild" % (L.qs_abi_version(), ABI_VERSION))
-    if (L.qs_sizeof_params(), L.qs_sizeof_state(), L.qs_sizeof_step_io()) != (C.sizeof(QsParams), C.sizeof(QsState), C.sizeof(QsStepIO)):
+    if (L.qs_sizeof_params(), L.qs_sizeof_state(), L.qs_sizeof_step_io(), L.qs_sizeof_rollout_io()) != \
+            (C.sizeof(QsParams), C.sizeof(QsState), C.sizeof(QsStepIO), C.sizeof(QsRolloutIO)):
         raise ImportError("libquadsim.so struct layout differs from the ctypes mirror: rebuild")
     _lib = L
     return L

@@ -4,7 +4,10 @@ Mirrors `BaseRLAviary` (gym_pybullet_drones/envs/BaseRLAviary.py:13-322).  The p
 Python loops of `_preprocessAction` / `_computeObs` live inside the fused CUDA step
 (qs_step): this class only declares the spaces and the kernel configuration.
 """
+import ctypes as C
+
 import numpy as np
+import torch
 
 from .. import _native as N
 from .._compat import spaces
@@ -84,3 +87,89 @@ class BaseRLAviary(BaseAviary):
         """Current observation (BaseRLAviary.py:284-322): [D, 12+B*A] ndarray, or the [E, D, .] tensor."""
         obs = self._obs_buf[self._cur]
         return self._shape_obs(obs) if self.VECTORIZED else self._obs_to_host_single(obs)
+
+    ################################################################################
+
+    def rollout(self, actions=None, num_steps=None, seed=0, out=None):
+        """T control ticks in one kernel launch (qs_rollout): exactly `num_steps` calls of `step()` with the same
+        actions, but the drone state stays in registers and the action history in shared memory between ticks.
+
+        Vector API only.  `actions`: float32 CUDA tensor [T, E, D, A], or None for uniform[-1, 1) actions generated on the
+        device from (`seed`, tick, drone) -- the synthetic random-action workload.  Autoreset must be "same_step" or
+        disabled; `info["final_obs"]` is not produced.  Returns a dict of CUDA tensors in rollout-buffer layout:
+        obs [T, E, D, obs_dim] (observation AFTER each tick), actions [T, E, D, A], rewards / terminated / truncated [T, E].
+        `out` may pass a previous result dict to reuse its buffers."""
+        if not self.VECTORIZED:
+            raise ValueError("rollout() needs the vector API (num_envs=...)")
+        if self._flags & N.FLAG_AUTORESET_NEXT_STEP:
+            raise ValueError("rollout() supports autoreset='same_step' or disabled")
+        if self._dw_fz is not None:
+            raise ValueError("rollout() needs drones_per_env <= 128")
+        E, D, A, od, dev = self._E, self._D, self._A, self._obs_dim, self.device
+        if actions is not None:
+            actions = actions.to(device=dev, dtype=torch.float32).contiguous()
+            T = actions.shape[0]
+            if tuple(actions.shape[1:]) not in ((E, D, A), (E * D, A)):
+                raise ValueError("actions must be [T, %d, %d, %d]" % (E, D, A))
+        else:
+            T = int(num_steps)
+        if out is None or out["obs"].shape[0] != T:
+            out = dict(obs=torch.empty((T, E, D, od), dtype=torch.float32, device=dev),
+                       actions=actions if actions is not None else torch.empty((T, E, D, A), dtype=torch.float32, device=dev),
+                       rewards=torch.empty((T, E), dtype=torch.float32, device=dev),
+                       terminated=torch.empty((T, E), dtype=torch.bool, device=dev),
+                       truncated=torch.empty((T, E), dtype=torch.bool, device=dev))
+        elif actions is not None:
+            out["actions"] = actions
+        tmax = self._lib.qs_rollout_max_ticks(self._act_type(), self._B, D)
+        if tmax <= 0:
+            raise ValueError("rollout() is not available for this observation width (action buffer too long for shared memory)")
+        io = N.QsRolloutIO()
+        io.seed, io.act_buffer_size = int(seed) & 0xFFFFFFFFFFFFFFFF, self._B
+        n = self._N
+        with self._on_device():
+            stream = self._stream()
+            k0 = 0
+            while k0 < T:
+                tt = min(tmax, T - k0)
+                cur = self._cur
+                io.actions = out["actions"][k0].data_ptr() if actions is not None else None
+                io.actions_out = out["actions"][k0].data_ptr() if actions is None else None
+                io.obs_init = self._obs_ptr[cur]
+                io.obs = out["obs"][k0].data_ptr()
+                io.obs_last = self._obs_ptr[1 - cur]
+                io.reward, io.terminated, io.truncated = out["rewards"][k0].data_ptr(), out["terminated"][k0].data_ptr(), out["truncated"][k0].data_ptr()
+                io.done = None
+                io.tick0, io.T = int(getattr(self, "_rollout_tick", 0)) + k0, tt
+                rc = self._lib.qs_rollout(C.byref(self._P), C.byref(self._st), C.byref(io), self._act_type(), self._task(),
+                                          E, D, self.PYB_STEPS_PER_CTRL, self._effects,
+                                          self._flags & ~N.FLAG_AUTORESET_NEXT_STEP, stream)
+                N.check(rc, "qs_rollout")
+                self._cur = 1 - cur
+                k0 += tt
+        self._rollout_tick = int(getattr(self, "_rollout_tick", 0)) + T
+        # keep the per-step outputs of the env consistent with the last tick
+        self._reward.copy_(out["rewards"][-1]); self._terminated.copy_(out["terminated"][-1]); self._truncated.copy_(out["truncated"][-1])
+        return out
+
+    @staticmethod
+    def rollout_actions_reference(seed, tick0, num_steps, n_drones, width):
+        """NumPy restatement of the device action generator (for tests / reproducibility):
+        splitmix64(seed + 2*((tick0+k)*N + i) + {0,1}) -> four uint32 -> (u >> 8) * 2^-23 - 1."""
+        M = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+        def sm64(x):
+            with np.errstate(over="ignore"):
+                x = (x + np.uint64(0x9E3779B97F4A7C15)) & M
+                z = x
+                z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M
+                z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M
+                return z ^ (z >> np.uint64(31))
+        k = np.arange(num_steps, dtype=np.uint64)[:, None]
+        i = np.arange(n_drones, dtype=np.uint64)[None, :]
+        with np.errstate(over="ignore"):
+            key = np.uint64(seed) + np.uint64(2) * ((np.uint64(tick0) + k) * np.uint64(n_drones) + i)
+        r0, r1 = sm64(key), sm64(key + np.uint64(1))
+        u = np.stack([r0 & np.uint64(0xFFFFFFFF), r0 >> np.uint64(32), r1 & np.uint64(0xFFFFFFFF), r1 >> np.uint64(32)], axis=-1)
+        f = ((u >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 8388608.0) - np.float32(1.0)).astype(np.float32)
+        return f[..., :width]

@@ -147,16 +147,43 @@ typedef struct QsStepIO {
                                    (only the split-substep protocol passes PYB_STEPS_PER_CTRL here) */
 } QsStepIO;
 
+/* Multi-tick rollout: T control ticks in ONE launch (the caller is SB3's collect_rollouts,
+ * examples/learn.py:93).  Exactly T calls of qs_step with SAME_STEP (or no) autoreset, but the drone state stays in
+ * registers and the action history in shared memory between ticks: per tick only the action is read and the observation
+ * row, reward and flags are written. */
+typedef struct QsRolloutIO {
+    const float* actions;       /* [T][N][A] float32, or NULL: uniform[-1,1) actions generated on the device from (seed, tick, drone) */
+    float* actions_out;         /* out [T][N][A] the actions that were applied; nullable */
+    const float* obs_init;      /* [N][12+B*A] observation before the first tick (source of the initial action history) */
+    float* obs;                 /* out [T][N][12+B*A] (PPO rollout-buffer layout) */
+    float* obs_last;            /* out [N][12+B*A] copy of the last tick's observation (the env's current observation); nullable */
+    float* reward;              /* out [T][E] */
+    unsigned char* terminated;  /* out [T][E] */
+    unsigned char* truncated;   /* out [T][E] */
+    unsigned char* done;        /* out [T][E]; nullable */
+    unsigned long long seed;    /* device action generator: splitmix64(seed + 2*((tick0+k)*N + drone) + {0,1}) */
+    long long tick0;            /* global index of the first tick of this launch (continues the generator's stream) */
+    int T;                      /* ticks in this launch; qs_rollout_max_ticks() bounds it (shared-memory window) */
+    int act_buffer_size;        /* B */
+} QsRolloutIO;
+
 int qs_abi_version(void);
 const char* qs_last_error(void);
 int qs_sizeof_params(void);
 int qs_sizeof_state(void);
 int qs_sizeof_step_io(void);
+int qs_sizeof_rollout_io(void);
 
 /* One control tick for n_envs aviaries of drones_per_env drones: action decode -> `substeps` x DYN ->
  * obs / reward / terminated / truncated (+ autoreset).  RL action types; task = QS_TASK_HOVER or NONE. */
 int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_type, int task,
             int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream);
+
+/* T fused control ticks (see QsRolloutIO).  RL action types, KIN observations, drones_per_env <= 128, autoreset SAME_STEP or
+ * none (flags as qs_step; final_obs is not produced).  qs_rollout_max_ticks gives the largest T for an observation width. */
+int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int act_type, int task,
+               int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream);
+int qs_rollout_max_ticks(int act_type, int act_buffer_size, int drones_per_env);
 
 /* CtrlAviary semantics: rpm[N][4] clipped to [0, MAX_RPM], `substeps` x DYN, optional [N][20] state vectors. */
 int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, float* state20_out, const float* dw_fz,

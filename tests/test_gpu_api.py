@@ -108,3 +108,65 @@ def test_policy_rollout_on_device_config3_shape():
     torch.cuda.synchronize()
     assert torch.isfinite(ret).all() and float(ret.mean()) > 0 and float(n_done) > 0
     assert int(env.step_counter.max()) <= 8 * 124
+
+
+@pytest.mark.parametrize("cls,act,D,phys,T", [("MultiHoverAviary", "RPM", 2, "DYN", 300), ("HoverAviary", "ONE_D_RPM", 1, "DYN", 40),
+                                              ("HoverAviary", "PID", 1, "DYN", 40), ("MultiHoverAviary", "RPM", 4, "PYB_GND_DRAG_DW", 24),
+                                              ("MultiHoverAviary", "VEL", 3, "PYB_DRAG", 24)])
+def test_rollout_is_bit_identical_to_steps(cls, act, D, phys, T):
+    """qs_rollout(T) == T x qs_step: observations, rewards, flags, final state planes, PID state and counters, bit for bit
+    (state in registers / history in a sliding shared-memory window vs HBM round trips).  T=300 also crosses the
+    shared-memory window limit, so the Python side splits the rollout into two launches."""
+    import gym_pybullet_drones_b200.envs as envs
+    from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
+    E = 300
+    kw = dict(physics=Physics[phys], act=ActionType[act], num_envs=E, autoreset="same_step")
+    if cls == "MultiHoverAviary":
+        kw["num_drones"] = D
+        if phys != "DYN":
+            kw["initial_xyzs"] = np.array([[0.05 * k, -0.03 * k, 0.3 + 1.5 * k] for k in range(D)])
+    e1, e2 = getattr(envs, cls)(**kw), getattr(envs, cls)(**kw)
+    A = e1._A
+    g = torch.Generator(device="cuda").manual_seed(11)
+    acts = torch.rand((T, E, D, A), device="cuda", generator=g) * 2 - 1
+    if act == "PID":
+        acts = acts * 0.3 + torch.tensor([0.0, 0.0, 0.8], device="cuda")
+    e1.reset(); e2.reset()
+    obs_l, rew_l, te_l, tr_l = [], [], [], []
+    for t in range(T):
+        o, r, te, tr, _ = e1.step(acts[t])
+        obs_l.append(o.clone()); rew_l.append(r.clone()); te_l.append(te.clone()); tr_l.append(tr.clone())
+    out = e2.rollout(acts)
+    assert torch.equal(out["obs"], torch.stack(obs_l)) and torch.equal(out["rewards"], torch.stack(rew_l))
+    assert torch.equal(out["terminated"], torch.stack(te_l)) and torch.equal(out["truncated"], torch.stack(tr_l))
+    assert torch.equal(e1._planes, e2._planes) and torch.equal(e1._step_counter, e2._step_counter)
+    assert torch.equal(e1._last_rpm, e2._last_rpm)
+    if e1._pid is not None:
+        assert torch.equal(e1._pid, e2._pid)
+    assert torch.equal(e1._obs_buf[e1._cur], e2._obs_buf[e2._cur])
+    if act == "RPM" and phys == "DYN":
+        assert bool((torch.stack(te_l) | torch.stack(tr_l)).any())      # autoreset exercised inside the rollout
+    # the envs stay interchangeable afterwards
+    o1, *_ = e1.step(acts[0]); o2, *_ = e2.step(acts[0])
+    assert torch.equal(o1, o2)
+
+
+def test_rollout_device_action_generator():
+    """actions=None: uniform[-1,1) actions from the counter-based device generator == its NumPy restatement, and the
+    rollout equals stepping with those actions; consecutive rollouts continue the stream."""
+    from gym_pybullet_drones_b200.envs import MultiHoverAviary
+    from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
+    E, D, T = 256, 2, 20
+    kw = dict(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E, autoreset="same_step")
+    e1, e2 = MultiHoverAviary(**kw), MultiHoverAviary(**kw)
+    e1.reset(); e2.reset()
+    outa = e2.rollout(num_steps=T, seed=1234)
+    a_ref = MultiHoverAviary.rollout_actions_reference(1234, 0, T, E * D, 4).reshape(T, E, D, 4)
+    assert np.array_equal(outa["actions"].cpu().numpy(), a_ref)
+    assert float(outa["actions"].min()) >= -1 and float(outa["actions"].max()) < 1 and abs(float(outa["actions"].mean())) < 0.01
+    for t in range(T):
+        o, *_ = e1.step(outa["actions"][t])
+        assert torch.equal(o, outa["obs"][t]), t
+    outb = e2.rollout(num_steps=5, seed=1234)
+    b_ref = MultiHoverAviary.rollout_actions_reference(1234, T, 5, E * D, 4).reshape(5, E, D, 4)
+    assert np.array_equal(outb["actions"].cpu().numpy(), b_ref)

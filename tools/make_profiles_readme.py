@@ -1,0 +1,67 @@
+"""Regenerates profiles/README.md from the latest bench / config / ncu artefacts (run in the build container)."""
+import glob
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+bench = sys.argv[1] if len(sys.argv) > 1 else sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "bench*.json")), key=os.path.getmtime)[-1]
+b = json.load(open(bench))
+ref = None
+for f in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "bench*_ref.json")), key=os.path.getmtime):
+    ref = json.load(open(f))
+cfg = {}
+if os.path.isfile(os.path.join(ROOT, "gpurun_out", "configs_r01.json")):
+    cfg = json.load(open(os.path.join(ROOT, "gpurun_out", "configs_r01.json")))
+    json.dump(cfg, open(os.path.join(ROOT, "profiles", "r01_configs.json"), "w"), indent=1)
+json.dump(b, open(os.path.join(ROOT, "profiles", "r01_bench_n1.json"), "w"), indent=1)
+if ref:
+    json.dump(ref, open(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.json"), "w"), indent=1)
+refcpu = json.load(open(os.path.join(ROOT, "profiles", "reference_cpu_r01.json")))
+L = []
+L.append("# profiles/ — round 1 measurements (B200, sm_100a)\n")
+L.append("Everything here is copied from `gpurun_out/` (scratch) by `tools/make_profiles_readme.py` / `tools/summarize_profile.py`.\n")
+L.append("## Headline bench line (`python bench.py`, N=1; file `r01_bench_n1.json`)\n")
+r = b["roofline"]
+L.append("| quantity | value |\n|---|---|")
+L.append("| workload | %s |" % b["config"]["workload"])
+L.append("| `value` (device-resident) | **%.3g drone-steps/s** (%.2f us per 65 536-drone step, %d steps) |" % (b["value"], b["ms_per_step"] * 1e3, b["steps"]))
+L.append("| `e2e` (NumPy API, H2D %d B + D2H %d B per step) | **%.3g drone-steps/s** |" % (b["e2e"]["h2d_bytes_per_step"], b["e2e"]["d2h_bytes_per_step"], b["e2e"]["value"]))
+L.append("| roofline (HBM, %s) | achieved %.0f GB/s of %.0f GB/s measured = **%.3f** (646 B x 65 536 / %.2f us) |" % (r.get("timing", "event pairs"), r["achieved"], r["peak"], r["frac"], r["kernel_ms"] * 1e3))
+L.append("| clocks during the timed region | %s |" % json.dumps(b.get("clocks")))
+if "cpu_baseline" in b:
+    L.append("| `cpu_baseline` (oracle port, 1 core of the GPU box) | %.3g drone-steps/s — %s |" % (b["cpu_baseline"]["value"], b["cpu_baseline"]["sample"]))
+if ref:
+    L.append("| `--impl reference` (oracle port, %d processes) | %.3g drone-steps/s |" % (ref["cpu_baseline"]["cores"], ref["value"]))
+L.append("| real reference, build container | %.0f drone-steps/s on one core (MultiHover D=2, S=8), %.0f on %d cores (`reference_cpu_r01.json`) |" %
+         (refcpu["cases"][2]["drone_steps_per_s"], refcpu["fan_out"]["drone_steps_per_s"], refcpu["fan_out"]["processes"]))
+ex = b.get("extras", {})
+L.append("\n### extras of the same run\n")
+L.append("| item | ms per step | drone-steps/s | algorithmic-bytes fraction of HBM peak |\n|---|---|---|---|")
+if "cuda_graph_replay" in ex and "ms_per_step" in ex["cuda_graph_replay"]:
+    g = ex["cuda_graph_replay"]
+    L.append("| same launches replayed from a CUDA graph | %.4f | %.3g | %.3f |" % (g["ms_per_step"], g["value"], 646 * 65536 / (g["ms_per_step"] * 1e-3) / 1e9 / r["peak"]))
+if "fused_rollout_T32" in ex and "ms_per_step" in ex["fused_rollout_T32"]:
+    g = ex["fused_rollout_T32"]
+    L.append("| `qs_rollout`, 32 ticks per launch | %.4f | %.3g | %.3f (algorithmic; the fusion removes the history re-read and the state round trip) |" % (g["ms_per_step"], g["value"], g["hbm_frac_algorithmic"]))
+for n, v in ex.get("drones_per_launch_sweep", {}).items():
+    if "ms_per_step" in v:
+        L.append("| step kernel at %s drones per launch | %.4f | %.3g | %.3f |" % (n, v["ms_per_step"], v["value"], v["hbm_frac"]))
+if "host_us_per_step_call" in ex:
+    L.append("\nHost cost of one `env.step(tensor)` call (64-drone env, GPU idle): %.1f us." % ex["host_us_per_step_call"])
+if cfg:
+    L.append("\n## Other BASELINE.json configs (`tools/bench_configs.py`, file `r01_configs.json`)\n")
+    L.append("| config | drones | S | ms per step | drone-steps/s | alg. bytes | HBM frac | note |\n|---|---|---|---|---|---|---|---|")
+    for k, v in cfg.items():
+        if "drone_steps_per_s" in v:
+            L.append("| %s | %s | %s | %.4f | %.3g | %s | %s | %s |" % (k, v.get("drones"), v.get("S"), v["ms_per_step"], v["drone_steps_per_s"], v.get("alg_bytes", "-"),
+                                                                   ("%.3f" % v["hbm_frac"]) if "hbm_frac" in v else ("%.3g pairs/s" % v["pairs_per_s"] if "pairs_per_s" in v else "-"), v.get("note", "")))
+        else:
+            L.append("| %s | n=%s | - | %.4f | %.3g calls/s | %s | %.3f | |" % (k, v["n"], v["ms_per_call"], v["calls_per_s"], v["alg_bytes"], v["hbm_frac"]))
+L.append("\n## ncu captures (`ncu --set full --clock-control none --import-source on`, one GPU, `bench.py --steps 20`)\n")
+for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_*_ncu.md"))):
+    L.append("* `%s` — %s" % (os.path.basename(f), open(f).read().split("\n")[2]))
+L.append("* `r01_a_launches.csv` — `ncu --metrics gpu__time_duration.sum` launch list of the first correct kernel (one `step_kernel` launch per env.step; the only other launches are torch fills/copies at setup).")
+L.append("\n`traffic` in the bench JSON: ncu's `dram__bytes_read.sum` is 24.3 MB per launch (state 4.2 MB + actions 1 MB + old observation span 18.9 MB = the algorithmic reads); `dram__bytes_write.sum` reads ~0 inside the kernel because the 23 MB of stores are still in the 126 MB write-back L2 when the kernel ends.")
+open(os.path.join(ROOT, "profiles", "README.md"), "w").write("\n".join(L) + "\n")
+print("\n".join(L))
