@@ -178,7 +178,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner on stdout when the first communicator is created: keep stdout for the one
+        # JSON line by pointing fd 1 at stderr while the process group comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from gym_pybullet_drones_b200.envs import MultiHoverAviary
     from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
