@@ -271,6 +271,12 @@ class BaseAviary(Env):
         self._h_term = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
         self._h_trunc = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
         self._hcur = 0
+        self._ev_small = torch.cuda.Event()
+        if self._final_obs is not None:
+            self._h_idx = torch.zeros((E,), dtype=torch.int64).pin_memory()
+            self._idx_dev = torch.zeros((E,), dtype=torch.int64, device=dev)
+            self._final_rows = torch.zeros((E, D, self._obs_dim), **f32)
+            self._h_final = torch.zeros((E, D, self._obs_dim), dtype=torch.float32).pin_memory()
 
     ################################################################################
     # state views (float32 CUDA tensors; names follow BaseAviary.py:470-476)
@@ -471,26 +477,36 @@ class BaseAviary(Env):
             k = self._hcur
             self._hcur = 1 - k
             h_obs, h_rew, h_te, h_tr = self._h_obs[k], self._h_reward[k], self._h_term[k], self._h_trunc[k]
-            h_obs.copy_(obs, non_blocking=True)
+            stream = torch.cuda.current_stream(self.device)
+            # small results first (their own event), then the observation rows: the host inspects the flags while the
+            # 19 MB copy is still on the wire, and queues the few terminal-observation rows behind it
             h_rew.copy_(self._reward, non_blocking=True)
             h_te.copy_(self._terminated, non_blocking=True)
             h_tr.copy_(self._truncated, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            o = h_obs.numpy().reshape(self._E, self._D, self._obs_dim)
+            self._ev_small.record(stream)
+            h_obs.copy_(obs, non_blocking=True)
+            self._ev_small.synchronize()
             rew, term, trunc = h_rew.numpy(), h_te.numpy(), h_tr.numpy()
-            if self._host_copy:
-                o, rew, term, trunc = o.copy(), rew.copy(), term.copy(), trunc.copy()
             info = {}
+            nd = 0
             if self._final_obs is not None:
                 done = term | trunc
                 info = {"_final_obs": done}
-                if done.any():
-                    # rare rows only: gather the finished aviaries' terminal observations on the device, one small D2H
-                    idx = np.flatnonzero(done)
-                    idx_dev = torch.from_numpy(idx).to(self.device, non_blocking=True)
-                    rows = torch.index_select(self._final_view, 0, idx_dev).cpu()
-                    info["final_obs"] = rows.numpy()          # [k, D, obs_dim], k = number of finished aviaries
-                    info["final_obs_env"] = idx                # their indices
+                idx = np.flatnonzero(done)
+                nd = idx.shape[0]
+                if nd:
+                    # finished aviaries only: gather their terminal observations on the device into pinned memory
+                    self._h_idx.numpy()[:nd] = idx
+                    self._idx_dev[:nd].copy_(self._h_idx[:nd], non_blocking=True)
+                    torch.index_select(self._final_view, 0, self._idx_dev[:nd], out=self._final_rows[:nd])
+                    self._h_final[:nd].copy_(self._final_rows[:nd], non_blocking=True)
+                    info["final_obs_env"] = idx                # indices of the finished aviaries
+            stream.synchronize()
+            o = h_obs.numpy().reshape(self._E, self._D, self._obs_dim)
+            if nd:
+                info["final_obs"] = self._h_final[:nd].numpy().copy()      # [k, D, obs_dim]
+            if self._host_copy:
+                o, rew, term, trunc = o.copy(), rew.copy(), term.copy(), trunc.copy()
             return o, rew, term, trunc, info
 
     def _single_result(self, obs):

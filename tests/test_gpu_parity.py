@@ -496,3 +496,37 @@ def test_abi_argument_errors():
     assert b"aligned" in L.qs_last_error()
     with pytest.raises(ValueError):
         N.check(-2, "x")
+
+
+@pytest.mark.parametrize("D,E,phys,eff", [(100, 7, "DYN", 0), (128, 3, "DYN", 0), (5, 103, "PYB_GND_DRAG_DW", 7)])
+def test_ragged_aviary_sizes_vs_oracle(D, E, phys, eff):
+    """Aviary sizes that do not divide the CTA (D=100 -> 100 live threads of 128; D=5 -> 125), a last CTA that is only
+    partly full, and the in-CTA downwash over D drones: 40 ticks against the oracle."""
+    _, _, _, MultiHoverAviary, ActionType, _, Physics, O = _imports()
+    T = 40
+    i = np.arange(D)
+    xyz = np.stack([0.4 * (i % 10) + 0.03 * (i // 10), 0.4 * ((i // 10) % 10), 0.3 + 1.5 * (i // 100) + 0.013 * i], axis=1) if eff == 0 else \
+        np.stack([0.05 * i, -0.03 * i, 0.3 + 1.5 * i], axis=1)
+    rng = np.random.default_rng(17)
+    acts = (0.5 * rng.uniform(-1, 1, (T, E, D, 4))).astype(np.float32)
+    env = MultiHoverAviary(num_drones=D, initial_xyzs=xyz, physics=Physics[phys], act=ActionType.RPM, num_envs=E)
+    ora = O.OracleAviary("multihover", E, D, act="rpm", initial_xyzs=xyz, effects=eff)
+    _compare_with_oracle(env, ora, acts, 2e-5)
+
+
+def test_set_pid_coefficients_changes_the_controller():
+    """BaseControl.setPIDCoefficients (BaseControl.py:138-177): new gains reach the kernel and match the oracle."""
+    DSLPIDControl, _, _, _, _, DroneModel, _, O = _imports()
+    n = 64
+    rng = np.random.default_rng(2)
+    pos, vel, tp = rng.uniform(-1, 1, (n, 3)), rng.uniform(-1, 1, (n, 3)), rng.uniform(-1, 1, (n, 3))
+    q = rng.normal(size=(n, 4)); q[:, 3] = np.abs(q[:, 3]) + 2; q /= np.linalg.norm(q, axis=1, keepdims=True)
+    ctrl = DSLPIDControl(DroneModel.CF2X, num_drones=n)
+    ora = O.OraclePID(n, "cf2x")
+    r0, _, _ = ctrl.computeControl(1 / 240, pos, q, vel, None, tp)
+    ctrl.reset()
+    ctrl.setPIDCoefficients(p_coeff_pos=np.array([.8, .8, 2.0]), d_coeff_att=np.array([10000., 10000., 6000.]))
+    ora.P_FOR = np.array([.8, .8, 2.0]); ora.D_TOR = np.array([10000., 10000., 6000.])
+    r1, pe, ye = ctrl.computeControl(1 / 240, pos, q, vel, None, tp)
+    o1, ope, oye = ora.compute(1 / 240, pos, q, vel, tp)
+    assert relerr(r1, o1) < 2e-5 and relerr(pe, ope) < 1e-6 and np.abs(r1 - r0).max() > 1.0
