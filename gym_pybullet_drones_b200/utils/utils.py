@@ -1,22 +1,29 @@
-"""Script helpers with the reference's names (gym_pybullet_drones/utils/utils.py:10-54)."""
+"""Script helpers under the reference's names (gym_pybullet_drones/utils/utils.py): `sync` paces a loop to the wall
+clock, `str2bool` parses argparse booleans."""
 import argparse
 import time
 
+_TRUE = {"yes", "true", "t", "y", "1"}
+_FALSE = {"no", "false", "f", "n", "0"}
+
 
 def sync(i, start_time, timestep):
-    """Paces a loop to the wall clock (utils.py:10-30)."""
-    if timestep > .04 or i % (int(1 / (24 * timestep))) == 0:
-        elapsed = time.time() - start_time
-        if elapsed < (i * timestep):
-            time.sleep(timestep * i - elapsed)
+    """Sleep so that iteration `i` of a loop with period `timestep` does not run ahead of real time.  Like the
+    reference, fast loops (period <= 40 ms) are only checked about 24 times per simulated second."""
+    stride = max(1, int(1.0 / (24.0 * timestep))) if timestep <= 0.04 else 1
+    if i % stride:
+        return
+    ahead = i * timestep - (time.time() - start_time)
+    if ahead > 0:
+        time.sleep(ahead)
 
 
 def str2bool(val):
-    """argparse boolean (utils.py:33-54)."""
     if isinstance(val, bool):
         return val
-    if val.lower() in ('yes', 'true', 't', 'y', '1'):
+    key = str(val).strip().lower()
+    if key in _TRUE:
         return True
-    if val.lower() in ('no', 'false', 'f', 'n', '0'):
+    if key in _FALSE:
         return False
     raise argparse.ArgumentTypeError("[ERROR] in str2bool(), a Boolean value is expected")
