@@ -72,8 +72,13 @@ class QsRolloutIO(C.Structure):
     ]
 
 
+class QsHostIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("action_host", "obs_host", "reward_host", "terminated_host", "truncated_host", "done_host",
+                                          "final_obs_host", "final_env_host", "n_final_host", "action_dev", "final_env_dev", "final_rows_dev")]
+
+
 EXPORTS = ["qs_abi_version", "qs_last_error", "qs_sizeof_params", "qs_sizeof_state", "qs_sizeof_step_io",
-           "qs_sizeof_rollout_io", "qs_step", "qs_rollout", "qs_rollout_max_ticks", "qs_dyn_substeps", "qs_pid_control",
+           "qs_sizeof_rollout_io", "qs_sizeof_host_io", "qs_step", "qs_step_host", "qs_rollout", "qs_rollout_max_ticks", "qs_dyn_substeps", "qs_pid_control",
            "qs_downwash", "qs_reset"]
 
 
@@ -113,6 +118,10 @@ def lib():
     L.qs_step.restype = C.c_int
     L.qs_step.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.POINTER(QsStepIO), C.c_int, C.c_int,
                           C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
+    L.qs_step_host.restype = C.c_int
+    L.qs_step_host.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.POINTER(QsStepIO), C.POINTER(QsHostIO), C.c_int, C.c_int,
+                               C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
+    L.qs_sizeof_host_io.restype = C.c_int
     L.qs_rollout.restype = C.c_int
     L.qs_rollout.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.POINTER(QsRolloutIO), C.c_int, C.c_int,
                              C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]

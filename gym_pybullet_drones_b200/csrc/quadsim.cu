@@ -13,6 +13,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include "quad_core.cuh"
 
@@ -861,6 +863,15 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ Rese
 
 constexpr size_t kStageLimit = 40 * 1024;      // bytes of staged rows per CTA (4 CTAs/SM must fit in 227 KB)
 
+// rows of the k finished aviaries -> compact buffer (one aviary = D*obs_dim contiguous floats)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, float* __restrict__ dst, int k, int row_floats) {
+    const int r = blockIdx.x;
+    if (r >= k) return;
+    const float* s = src + idx[r] * (long long)row_floats;
+    float* d = dst + (long long)r * row_floats;
+    for (int j = threadIdx.x; j < row_floats; j += blockDim.x) d[j] = s[j];
+}
+
 size_t step_smem_bytes(const StepArgs& a) {
     return kStepSmemFixed + (a.stage_rows ? (size_t)a.tpb * a.obs_dim * 4 + 32 : 0);
 }
@@ -1037,6 +1048,68 @@ int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int 
 #undef QS_RCASE
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_rollout launch");
+}
+
+int qs_sizeof_host_io(void) { return (int)sizeof(QsHostIO); }
+
+int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const QsHostIO* h, int act_type, int task,
+                 int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream) {
+    if (!io || !h) return fail(QS_ERR_NULL, "qs_step_host: NULL io");
+    if (!h->action_host || !h->obs_host || !h->reward_host || !h->terminated_host || !h->truncated_host || !h->action_dev)
+        return fail(QS_ERR_NULL, "qs_step_host: NULL host buffer / action_dev");
+    if (!io->obs || !io->reward || !io->terminated || !io->truncated) return fail(QS_ERR_NULL, "qs_step_host: NULL device buffer");
+    const int A = act_width(act_type);
+    if (A < 0) return fail(QS_ERR_ENUM, "qs_step_host: bad act_type");
+    const bool state20 = flags & QS_FLAG_OBS_STATE20;
+    const long long N = (long long)n_envs * drones_per_env;
+    const int od = state20 ? 20 : 12 + io->act_buffer_size * A;
+    const bool want_final = (flags & QS_FLAG_AUTORESET_SAME_STEP) && io->final_obs && h->final_obs_host;
+    if (want_final && (!io->done || !h->done_host || !h->final_env_host || !h->n_final_host || !h->final_env_dev || !h->final_rows_dev))
+        return fail(QS_ERR_NULL, "qs_step_host: final_obs transfer needs done / final_env / final_rows buffers");
+    cudaStream_t s = (cudaStream_t)stream;
+    static const bool trace = getenv("QS_TRACE") != nullptr;
+    static int trace_n = 0;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double t0 = trace ? now() : 0.0;
+    double t1 = 0, t2 = 0, t3 = 0;
+    cudaError_t e = cudaMemcpyAsync(h->action_dev, h->action_host, (size_t)N * A * 4, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return cuda_fail(e, "qs_step_host H2D action");
+    QsStepIO dio = *io;
+    dio.action = h->action_dev;
+    if (int rc = qs_step(p, st, &dio, act_type, task, n_envs, drones_per_env, substeps, effects, flags, stream)) return rc;
+    cudaMemcpyAsync(h->reward_host, io->reward, (size_t)n_envs * 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(h->terminated_host, io->terminated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(h->truncated_host, io->truncated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
+    if (io->done && h->done_host) cudaMemcpyAsync(h->done_host, io->done, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
+    if (want_final) {
+        // the flags are 100 KB: wait for them, pick the finished aviaries, and queue their rows behind the observation copy
+        if (trace) t1 = now();
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return cuda_fail(e, "qs_step_host sync(flags)");
+        if (trace) t2 = now();
+        int k = 0;
+        for (int ev = 0; ev < n_envs; ++ev)
+            if (h->done_host[ev]) h->final_env_host[k++] = ev;
+        *h->n_final_host = k;
+        cudaMemcpyAsync(h->obs_host, io->obs, (size_t)N * od * 4, cudaMemcpyDeviceToHost, s);
+        if (k > 0) {
+            const int row_floats = drones_per_env * od;
+            cudaMemcpyAsync(h->final_env_dev, h->final_env_host, (size_t)k * 8, cudaMemcpyHostToDevice, s);
+            gather_rows_kernel<<<k, 128, 0, s>>>(io->final_obs, h->final_env_dev, h->final_rows_dev, k, row_floats);
+            cudaMemcpyAsync(h->final_obs_host, h->final_rows_dev, (size_t)k * row_floats * 4, cudaMemcpyDeviceToHost, s);
+        }
+    } else {
+        if (h->n_final_host) *h->n_final_host = 0;
+        cudaMemcpyAsync(h->obs_host, io->obs, (size_t)N * od * 4, cudaMemcpyDeviceToHost, s);
+    }
+    if (trace) t3 = now();
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cuda_fail(e, "qs_step_host sync");
+    if (trace && (++trace_n % 50) == 0)
+        fprintf(stderr, "[qs_step_host] enqueue1 %.0f us, sync(flags) %.0f us, scan+enqueue2 %.0f us, final sync %.0f us, n_final %d\n",
+                t1 - t0, t2 - t1, t3 - t2, now() - t3, h->n_final_host ? *h->n_final_host : -1);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "qs_step_host");
 }
 
 int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, float* state20_out, const float* dw_fz,

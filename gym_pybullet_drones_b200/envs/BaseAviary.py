@@ -271,12 +271,29 @@ class BaseAviary(Env):
         self._h_term = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
         self._h_trunc = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
         self._hcur = 0
-        self._ev_small = torch.cuda.Event()
+        self._h_done = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
+        self._h_nfinal = np.zeros(1, np.int32)
+        self._h_idx = torch.zeros((E,), dtype=torch.int64).pin_memory()
+        self._idx_dev = torch.zeros((E,), dtype=torch.int64, device=dev)
         if self._final_obs is not None:
-            self._h_idx = torch.zeros((E,), dtype=torch.int64).pin_memory()
-            self._idx_dev = torch.zeros((E,), dtype=torch.int64, device=dev)
             self._final_rows = torch.zeros((E, D, self._obs_dim), **f32)
             self._h_final = torch.zeros((E, D, self._obs_dim), dtype=torch.float32).pin_memory()
+        self._h_action_np = self._h_action.numpy()
+        self._h_idx_np = self._h_idx.numpy()
+        self._h_final_np = self._h_final.numpy() if self._final_obs is not None else None
+        self._hio, self._h_np = [], []
+        for k in range(2):
+            h = N.QsHostIO()
+            h.action_host, h.obs_host = self._h_action.data_ptr(), self._h_obs[k].data_ptr()
+            h.reward_host, h.terminated_host = self._h_reward[k].data_ptr(), self._h_term[k].data_ptr()
+            h.truncated_host, h.done_host = self._h_trunc[k].data_ptr(), self._h_done[k].data_ptr()
+            h.final_env_host, h.n_final_host = self._h_idx.data_ptr(), self._h_nfinal.ctypes.data
+            h.action_dev, h.final_env_dev = self._action_dev.data_ptr(), self._idx_dev.data_ptr()
+            if self._final_obs is not None:
+                h.final_obs_host, h.final_rows_dev = self._h_final.data_ptr(), self._final_rows.data_ptr()
+            self._hio.append(h)
+            self._h_np.append((self._h_obs[k].numpy().reshape(E, D, self._obs_dim), self._h_reward[k].numpy(),
+                               self._h_term[k].numpy(), self._h_trunc[k].numpy()))
 
     ################################################################################
     # state views (float32 CUDA tensors; names follow BaseAviary.py:470-476)
@@ -469,6 +486,8 @@ class BaseAviary(Env):
                 return self._shape_obs(obs), self._reward, self._terminated, self._truncated, info
             #### NumPy path: pinned H2D of the action, D2H of the results, all inside this call ####
             a_np = np.asarray(action, dtype=np.float32).reshape(self._N, self._A)
+            if self.VECTORIZED and self._simple_launch:
+                return self._step_host(a_np)
             self._h_action.numpy()[...] = a_np
             self._action_dev.copy_(self._h_action, non_blocking=True)
             obs = self._launch(self._action_dev)
@@ -477,37 +496,42 @@ class BaseAviary(Env):
             k = self._hcur
             self._hcur = 1 - k
             h_obs, h_rew, h_te, h_tr = self._h_obs[k], self._h_reward[k], self._h_term[k], self._h_trunc[k]
-            stream = torch.cuda.current_stream(self.device)
-            # small results first (their own event), then the observation rows: the host inspects the flags while the
-            # 19 MB copy is still on the wire, and queues the few terminal-observation rows behind it
+            h_obs.copy_(obs, non_blocking=True)
             h_rew.copy_(self._reward, non_blocking=True)
             h_te.copy_(self._terminated, non_blocking=True)
             h_tr.copy_(self._truncated, non_blocking=True)
-            self._ev_small.record(stream)
-            h_obs.copy_(obs, non_blocking=True)
-            self._ev_small.synchronize()
-            rew, term, trunc = h_rew.numpy(), h_te.numpy(), h_tr.numpy()
-            info = {}
-            nd = 0
-            if self._final_obs is not None:
-                done = term | trunc
-                info = {"_final_obs": done}
-                idx = np.flatnonzero(done)
-                nd = idx.shape[0]
-                if nd:
-                    # finished aviaries only: gather their terminal observations on the device into pinned memory
-                    self._h_idx.numpy()[:nd] = idx
-                    self._idx_dev[:nd].copy_(self._h_idx[:nd], non_blocking=True)
-                    torch.index_select(self._final_view, 0, self._idx_dev[:nd], out=self._final_rows[:nd])
-                    self._h_final[:nd].copy_(self._final_rows[:nd], non_blocking=True)
-                    info["final_obs_env"] = idx                # indices of the finished aviaries
-            stream.synchronize()
+            torch.cuda.current_stream(self.device).synchronize()
             o = h_obs.numpy().reshape(self._E, self._D, self._obs_dim)
-            if nd:
-                info["final_obs"] = self._h_final[:nd].numpy().copy()      # [k, D, obs_dim]
+            rew, term, trunc = h_rew.numpy(), h_te.numpy(), h_tr.numpy()
             if self._host_copy:
                 o, rew, term, trunc = o.copy(), rew.copy(), term.copy(), trunc.copy()
-            return o, rew, term, trunc, info
+            return o, rew, term, trunc, {}
+
+    def _step_host(self, a_np):
+        """One qs_step_host call: every host<->device copy of the tick happens inside the C library."""
+        k = self._hcur
+        self._hcur = 1 - k
+        self._h_action_np[...] = a_np
+        io, cur, h = self._io, self._cur, self._hio[k]
+        io.obs_prev = self._obs_ptr[cur]
+        io.obs = self._obs_ptr[1 - cur]
+        rc = self._lib.qs_step_host(*self._step_head[:3], C.byref(h), *self._step_head[3:], torch.cuda.current_stream().cuda_stream)
+        if rc:
+            N.check(rc, "qs_step_host")
+        self._cur = 1 - cur
+        o, rew, term, trunc = self._h_np[k]
+        info = {}
+        if self._final_obs is not None:
+            nd = int(self._h_nfinal[0])
+            info = {"_final_obs": term | trunc}
+            if nd:
+                info["final_obs_env"] = self._h_idx_np[:nd]                      # indices of the finished aviaries
+                info["final_obs"] = self._h_final_np[:nd]                        # their terminal observations [k, D, obs_dim]
+        if self._host_copy:
+            o, rew, term, trunc = o.copy(), rew.copy(), term.copy(), trunc.copy()
+            if "final_obs" in info:
+                info["final_obs"], info["final_obs_env"] = info["final_obs"].copy(), info["final_obs_env"].copy()
+        return o, rew, term, trunc, info
 
     def _single_result(self, obs):
         o = self._obs_to_host_single(obs)

@@ -167,17 +167,41 @@ typedef struct QsRolloutIO {
     int act_buffer_size;        /* B */
 } QsRolloutIO;
 
+/* Host-buffer variant of one control tick (what a CPU-side caller such as SB3's DummyVecEnv loop sees): pinned host
+ * arrays in, pinned host arrays out, every host<->device copy inside the call. */
+typedef struct QsHostIO {
+    const float* action_host;        /* [N][A]  (pinned) */
+    float* obs_host;                 /* out [N][obs_dim] */
+    float* reward_host;              /* out [E] */
+    unsigned char* terminated_host;  /* out [E] */
+    unsigned char* truncated_host;   /* out [E] */
+    unsigned char* done_host;        /* out [E] */
+    float* final_obs_host;           /* out: rows [k][D][obs_dim] of the k aviaries that finished (SAME_STEP autoreset); nullable */
+    long long* final_env_host;       /* out [E]: their aviary indices, ascending (pinned; doubles as the upload staging) */
+    int* n_final_host;               /* out: k */
+    float* action_dev;               /* caller-owned device scratch [N][A] */
+    long long* final_env_dev;        /* caller-owned device scratch [E] */
+    float* final_rows_dev;           /* caller-owned device scratch [E][D][obs_dim] */
+} QsHostIO;
+
 int qs_abi_version(void);
 const char* qs_last_error(void);
 int qs_sizeof_params(void);
 int qs_sizeof_state(void);
 int qs_sizeof_step_io(void);
 int qs_sizeof_rollout_io(void);
+int qs_sizeof_host_io(void);
 
 /* One control tick for n_envs aviaries of drones_per_env drones: action decode -> `substeps` x DYN ->
  * obs / reward / terminated / truncated (+ autoreset).  RL action types; task = QS_TASK_HOVER or NONE. */
 int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_type, int task,
             int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream);
+
+/* qs_step with host buffers: H2D(action) -> fused tick -> D2H(reward, flags) -> D2H(obs) (+ a compact D2H of the terminal
+ * observations of finished aviaries).  `io` carries the device buffers exactly as for qs_step (io->action is ignored).
+ * Unlike every other entry point this one SYNCHRONISES `stream` before returning (the host arrays are valid on return). */
+int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const QsHostIO* h, int act_type, int task,
+                 int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream);
 
 /* T fused control ticks (see QsRolloutIO).  RL action types, KIN observations, drones_per_env <= 128, autoreset SAME_STEP or
  * none (flags as qs_step; final_obs is not produced).  qs_rollout_max_ticks gives the largest T for an observation width. */
