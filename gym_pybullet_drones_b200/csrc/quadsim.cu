@@ -420,8 +420,8 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
             float* row = stage_s + (size_t)t * od;
             const float* h = head_s + (size_t)t * 12;
             const unsigned char mode = mode_s[t];
-            if (mode & 1) {                                   // NEXT_STEP reset tick: history is NOT shifted
-                for (int k = od - 1; k >= 12; --k) row[k + A] = row[k];
+            if (mode & 1) {                                   // NEXT_STEP reset tick: history is NOT shifted (or is cleared)
+                for (int k = od - 1; k >= 12; --k) row[k + A] = (mode & 4) ? 0.f : row[k];
             } else if (A == 4) {
                 *reinterpret_cast<float4*>(row + od) = make_float4(act[0], act[1], act[2], act[3]);
             } else if (A == 3) {
@@ -435,17 +435,14 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
             } else {
                 for (int k = 0; k < 12; ++k) row[A + k] = h[k];
             }
-            if (mode & 2) {                                   // SAME_STEP autoreset: terminal observation's history
-                float* f = a.io.final_obs + i * od;
-                for (int k = 12; k < od; ++k) f[k] = row[k + A];
-            }
-            if (mode & 4) for (int k = 12; k < od; ++k) row[k + A] = 0.f;
         }
         __syncthreads();
+        const bool clear_hist = a.flags & QS_FLAG_AUTORESET_CLEARS_HISTORY;
+        const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
         if (A == 4) {
             const float4* src = reinterpret_cast<const float4*>(stage_s) + 1;
             float4* out = reinterpret_cast<float4*>(a.io.obs + c0 * od);
-            const int n4 = rows * (od >> 2);
+            const int c4n = od >> 2, n4 = rows * c4n;
             const int nt = blockDim.x;
             int j = t;
             for (; j + 5 * nt < n4; j += 6 * nt) {            // 6 independent LDS.128 in flight, then 6 coalesced STG.128
@@ -453,10 +450,30 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
                 out[j] = v0; out[j + nt] = v1; out[j + 2 * nt] = v2; out[j + 3 * nt] = v3; out[j + 4 * nt] = v4; out[j + 5 * nt] = v5;
             }
             for (; j < n4; j += nt) out[j] = src[j];
+            // SAME_STEP autoreset: the history part of the terminal observation of finished rows, one warp per row
+            if (a.io.final_obs && (a.flags & QS_FLAG_AUTORESET_SAME_STEP)) {
+                float4* fin = reinterpret_cast<float4*>(a.io.final_obs + c0 * od);
+                for (int r = warp; r < rows; r += nwarps)
+                    if (mode_s[r] & 2)
+                        for (int c = 3 + lane; c < c4n; c += 32) fin[r * c4n + c] = src[r * c4n + c];
+            }
         } else {
             const float* src = stage_s + A;
             float* out = a.io.obs + c0 * od;
             for (int j = t; j < rows * od; j += blockDim.x) out[j] = src[j];
+            if (a.io.final_obs && (a.flags & QS_FLAG_AUTORESET_SAME_STEP)) {
+                float* fin = a.io.final_obs + c0 * od;
+                for (int r = warp; r < rows; r += nwarps)
+                    if (mode_s[r] & 2)
+                        for (int c = 12 + lane; c < od; c += 32) fin[r * od + c] = src[r * od + c];
+            }
+        }
+        if (clear_hist) {                                     // optional: the observation after a reset carries an empty action buffer
+            __syncthreads();
+            if (live && (mode_s[t] & 4) && !(mode_s[t] & 1)) {
+                float* orow = a.io.obs + i * od;
+                for (int k = 12; k < od; ++k) orow[k] = 0.f;
+            }
         }
         return;
     }

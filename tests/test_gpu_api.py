@@ -112,7 +112,7 @@ def test_policy_rollout_on_device_config3_shape():
 
 @pytest.mark.parametrize("cls,act,D,phys,T", [("MultiHoverAviary", "RPM", 2, "DYN", 300), ("HoverAviary", "ONE_D_RPM", 1, "DYN", 40),
                                               ("HoverAviary", "PID", 1, "DYN", 40), ("MultiHoverAviary", "RPM", 4, "PYB_GND_DRAG_DW", 24),
-                                              ("MultiHoverAviary", "VEL", 3, "PYB_DRAG", 24)])
+                                              ("MultiHoverAviary", "VEL", 3, "PYB_DRAG", 24), ("HoverAviary", "PID+clear", 1, "DYN", 60)])
 def test_rollout_is_bit_identical_to_steps(cls, act, D, phys, T):
     """qs_rollout(T) == T x qs_step: observations, rewards, flags, final state planes, PID state and counters, bit for bit
     (state in registers / history in a sliding shared-memory window vs HBM round trips).  T=300 also crosses the
@@ -120,7 +120,11 @@ def test_rollout_is_bit_identical_to_steps(cls, act, D, phys, T):
     import gym_pybullet_drones_b200.envs as envs
     from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
     E = 300
+    clear = act.endswith("+clear")
+    act = act.split("+")[0]
     kw = dict(physics=Physics[phys], act=ActionType[act], num_envs=E, autoreset="same_step")
+    if clear:
+        kw.update(autoreset_clears_action_buffer=True, autoreset_clears_controllers=True)
     if cls == "MultiHoverAviary":
         kw["num_drones"] = D
         if phys != "DYN":
@@ -130,7 +134,7 @@ def test_rollout_is_bit_identical_to_steps(cls, act, D, phys, T):
     g = torch.Generator(device="cuda").manual_seed(11)
     acts = torch.rand((T, E, D, A), device="cuda", generator=g) * 2 - 1
     if act == "PID":
-        acts = acts * 0.3 + torch.tensor([0.0, 0.0, 0.8], device="cuda")
+        acts = acts * (torch.tensor([2.5, 2.5, 0.5], device="cuda") if clear else 0.3) + torch.tensor([0.0, 0.0, 0.8], device="cuda")
     e1.reset(); e2.reset()
     obs_l, rew_l, te_l, tr_l = [], [], [], []
     for t in range(T):

@@ -530,3 +530,59 @@ def test_set_pid_coefficients_changes_the_controller():
     r1, pe, ye = ctrl.computeControl(1 / 240, pos, q, vel, None, tp)
     o1, ope, oye = ora.compute(1 / 240, pos, q, vel, tp)
     assert relerr(r1, o1) < 2e-5 and relerr(pe, ope) < 1e-6 and np.abs(r1 - r0).max() > 1.0
+
+
+@pytest.mark.parametrize("mode", ["same_step", "next_step"])
+def test_autoreset_can_clear_action_buffer_and_controllers(mode):
+    """The reference's reset() keeps the action buffer and the embedded PID state; the opt-in flags clear
+    them when an aviary auto-resets.  Oracle loop with the same clearing done by hand."""
+    _, _, HoverAviary, _, ActionType, _, Physics, O = _imports()
+    E, T = 256, 420
+    rng = np.random.default_rng(91)
+    # one fixed far-away set-point per aviary: the drone flies out of the |x|,|y| <= 1.5 box, is truncated, resets, flies again
+    sp = (np.array([0, 0, 1.0], np.float32) + rng.choice([-1.0, 1.0], (E, 1, 3)).astype(np.float32) * np.array([3.0, 3.0, 0.3], np.float32)).astype(np.float32)
+    acts = np.broadcast_to(sp, (T, E, 1, 3)).copy()
+    env = HoverAviary(physics=Physics.DYN, act=ActionType.PID, pyb_freq=240, ctrl_freq=120, num_envs=E, autoreset=mode,
+                      autoreset_clears_action_buffer=True, autoreset_clears_controllers=True)
+    ora = O.OracleAviary("hover", E, 1, act="pid", ctrl_freq=120)
+    env.reset(); ora.reset()
+    pending = np.zeros(E, bool)
+    n_resets = 0
+
+    def clear(mask):
+        for b in ora.action_buffer:
+            b[mask] = 0
+        ora.ctrl.reset(mask=mask)
+
+    for t in range(T):
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(acts[t]).cuda())
+        if mode == "next_step" and pending.any():
+            snap = {f: getattr(ora, f).copy() for f in ("pos", "quat", "vel", "rpy_rates", "ang_v", "rpy", "last_clipped_action")}
+            sc, buf = ora.step_counter.copy(), [b.copy() for b in ora.action_buffer]
+            pid = [a.copy() for a in (ora.ctrl.integral_pos_e, ora.ctrl.last_rpy, ora.ctrl.integral_rpy_e)]
+            o_obs, o_rew, o_term, o_trunc = ora.step(acts[t])
+            for f, v in snap.items():
+                getattr(ora, f)[pending] = v[pending]
+            ora.step_counter[pending] = sc[pending]
+            for bn, bo in zip(ora.action_buffer, buf):
+                bn[pending] = bo[pending]
+            for a_new, a_old in zip((ora.ctrl.integral_pos_e, ora.ctrl.last_rpy, ora.ctrl.integral_rpy_e), pid):
+                a_new[pending] = a_old[pending]
+            clear(pending)
+            o_obs[pending] = ora.reset(mask=pending)[pending]
+            o_rew[pending] = 0; o_term[pending] = False; o_trunc[pending] = False
+        else:
+            o_obs, o_rew, o_term, o_trunc = ora.step(acts[t])
+        done = o_term | o_trunc
+        assert np.array_equal((term | trunc).cpu().numpy(), done), t
+        if mode == "same_step" and done.any():
+            assert relerr(info["final_obs"].cpu().numpy()[done], o_obs[done]) < 5e-5
+            clear(done)
+            o_obs = ora.reset(mask=done)
+            assert np.all(obs.cpu().numpy()[done][..., 12:] == 0)
+        n_resets += int(done.sum())
+        assert relerr(obs.cpu().numpy(), o_obs) < 5e-5, t
+        pending = done if mode == "next_step" else pending
+    assert n_resets > E // 2
+    pid_dev = env._pid.view(9, E).double().cpu().numpy()
+    assert relerr(pid_dev[0:3].T, ora.ctrl.integral_pos_e) < 1e-4 and relerr(pid_dev[6:9].T, ora.ctrl.integral_rpy_e) < 1e-3
