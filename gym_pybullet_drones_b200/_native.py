@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libquadsim.so")
+LIB_PATH = os.environ.get("QS_LIBQUADSIM", os.path.join(_HERE, "libquadsim.so"))    # override: A/B builds in tools/
 SOURCES = [os.path.join(_HERE, "csrc", "quadsim.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "quad_core.cuh"), os.path.join(_ROOT, "include", "quadsim.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -106,12 +106,25 @@ QS_HD void quat_to_euler(double x, double y, double z, double w, double& roll, d
 }
 
 // cos(theta) and sin(theta)/|w| for theta = |w| dt/2, from n2 = |w|^2 -- both are even in theta, so for the
-// small angles of a 240 Hz substep they are 8-term series in theta^2 (error < 1e-18 for theta^2 < 0.25):
+// small angles of a 240 Hz substep they are 5- or 8-term series in theta^2 (truncation < 2^-53 in both ranges):
 // no sqrt, no division, no range reduction.  Large rates fall back to sqrt/sincos.
 QS_HD void half_angle_terms(double n2, double dt, double& c, double& s_over_n) {
     const double h = 0.5 * dt;
     const double t = n2 * h * h;                 // theta^2
-    if (t < 0.25) {
+    if (t < 0.0078125) {
+        // theta^2 < 1/128 (|w| < 42 rad/s at 240 Hz): 5 terms are exact to double rounding (next terms t^5/10! < 8e-18)
+        double pc = 1.0 / 40320.0;                           // k=4  +1/8!
+        pc = pc * t - 1.0 / 720.0;                           // k=3  -1/6!
+        pc = pc * t + 1.0 / 24.0;                            // k=2  +1/4!
+        pc = pc * t - 0.5;                                   // k=1  -1/2!
+        c = pc * t + 1.0;                                    // k=0
+        double ps = 1.0 / 362880.0;                          // k=4  +1/9!
+        ps = ps * t - 1.0 / 5040.0;                          // k=3  -1/7!
+        ps = ps * t + 1.0 / 120.0;                           // k=2  +1/5!
+        ps = ps * t - 1.0 / 6.0;                             // k=1  -1/3!
+        ps = ps * t + 1.0;                                   // k=0
+        s_over_n = ps * h;
+    } else if (t < 0.25) {
         // cos(theta) = sum_{k=0..7} (-1)^k t^k/(2k)!
         double pc = -1.0 / 87178291200.0;                    // k=7  -1/14!
         pc = pc * t + 1.0 / 479001600.0;                     // k=6  +1/12!
@@ -191,12 +204,15 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
         d.qx *= inv; d.qy *= inv; d.qz *= inv; d.qw *= inv;
     }
     double q0x = d.qx, q0y = d.qy, q0z = d.qz, q0w = d.qw;                           // attitude at the start of the last substep
+    // per-tick constants of the Euler step: dt*J^-1, the gyroscopic differences (w x Jw for a diagonal J), dt/M*gravity
+    const double dj0 = dt * P.j_inv[0], dj1 = dt * P.j_inv[1], dj2 = dt * P.j_inv[2];
+    const double g21 = P.j[2] - P.j[1], g02 = P.j[0] - P.j[2], g10 = P.j[1] - P.j[0];
+    const double gm = dt_m * P.gravity;
     for (int s = 0; s < substeps; ++s) {
         q0x = d.qx; q0y = d.qy; q0z = d.qz; q0w = d.qw;
         const double x = d.qx, y = d.qy, z = d.qz, w = d.qw;
-        const double dd = x * x + y * y + z * z + w * w;
-        const double sc = 2.0 * (2.0 - dd);                                          // = 2/|q|^2  (:836, Bullet setRotation)
-        const double xs = x * sc, ys = y * sc, zs = z * sc;
+        // Bullet's s = 2/|q|^2 (:836): |q|^2 = 1 to 1e-16 for the whole tick (unit on entry, _integrateQ is norm preserving)
+        const double xs = x + x, ys = y + y, zs = z + z;
         // third column and third row of R
         const double r02 = x * zs + w * ys, r12 = y * zs - w * xs, r22 = 1.0 - (x * xs + y * ys);
         if (EFF & QS_EFFECT_GND) {                                                   // :715-750 on the substep-start state
@@ -219,28 +235,35 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
             tx = (P.sx[0] * f0 + P.sx[1] * f1 + P.sx[2] * f2 + P.sx[3] * f3) * P.kx;
             ty = (P.sy[0] * f0 + P.sy[1] * f1 + P.sy[2] * f2 + P.sy[3] * f3) * P.ky;
         }
-        double fx = r02 * thrust, fy = r12 * thrust, fz = r22 * thrust - P.gravity;  // :840-841
-        if (EFF & QS_EFFECT_DRAG) {                                                  // world force = -DRAG_COEFF*sum (.) vel
-            fx += (-1.0 * P.drag_coeff[0] * drag_sum) * d.vx;
-            fy += (-1.0 * P.drag_coeff[1] * drag_sum) * d.vy;
-            fz += (-1.0 * P.drag_coeff[2] * drag_sum) * d.vz;
-            if (s == 0) {
-                const double k = 2.0 * 3.14159265358979323846;
-                drag_sum = k * rpm[0] / 60.0 + k * rpm[1] / 60.0 + k * rpm[2] / 60.0 + k * rpm[3] / 60.0;
+        if (EFF == 0) {
+            // v += dt (R[:,2] thrust - [0,0,GRAVITY]) / M   (:840-841,:858,:860), one FMA per axis
+            const double tm = dt_m * thrust;
+            d.vx = d.vx + r02 * tm;
+            d.vy = d.vy + r12 * tm;
+            d.vz = d.vz + (r22 * tm - gm);
+        } else {
+            double fx = r02 * thrust, fy = r12 * thrust, fz = r22 * thrust - P.gravity;  // :840-841
+            if (EFF & QS_EFFECT_DRAG) {                                                  // world force = -DRAG_COEFF*sum (.) vel
+                fx += (-1.0 * P.drag_coeff[0] * drag_sum) * d.vx;
+                fy += (-1.0 * P.drag_coeff[1] * drag_sum) * d.vy;
+                fz += (-1.0 * P.drag_coeff[2] * drag_sum) * d.vz;
+                if (s == 0) {
+                    const double k = 2.0 * 3.14159265358979323846;
+                    drag_sum = k * rpm[0] / 60.0 + k * rpm[1] / 60.0 + k * rpm[2] / 60.0 + k * rpm[3] / 60.0;
+                }
             }
+            if (EFF & QS_EFFECT_DW) { fx += r02 * dw_fz; fy += r12 * dw_fz; fz += r22 * dw_fz; }
+            d.vx = d.vx + dt_m * fx;                                                     // :858,:860
+            d.vy = d.vy + dt_m * fy;
+            d.vz = d.vz + dt_m * fz;
         }
-        if (EFF & QS_EFFECT_DW) { fx += r02 * dw_fz; fy += r12 * dw_fz; fz += r22 * dw_fz; }
-        // torques - w x (J w)  (:856), w' = J^-1 torques (:857)
-        const double jwx = P.j[0] * d.wx, jwy = P.j[1] * d.wy, jwz = P.j[2] * d.wz;
-        const double ttx = tx - (d.wy * jwz - d.wz * jwy);
-        const double tty = ty - (d.wz * jwx - d.wx * jwz);
-        const double ttz = tz - (d.wx * jwy - d.wy * jwx);
-        d.vx = d.vx + dt_m * fx;                                                     // :858,:860
-        d.vy = d.vy + dt_m * fy;
-        d.vz = d.vz + dt_m * fz;
-        d.wx = d.wx + dt * (P.j_inv[0] * ttx);                                       // :861
-        d.wy = d.wy + dt * (P.j_inv[1] * tty);
-        d.wz = d.wz + dt * (P.j_inv[2] * ttz);
+        // w' = J^-1 (torques - w x (J w))  (:856-857); for the diagonal J: (w x Jw)_x = (Jz - Jy) wy wz, cyclic
+        const double ttx = tx - g21 * (d.wy * d.wz);
+        const double tty = ty - g02 * (d.wz * d.wx);
+        const double ttz = tz - g10 * (d.wx * d.wy);
+        d.wx = d.wx + dj0 * ttx;                                                     // :861
+        d.wy = d.wy + dj1 * tty;
+        d.wz = d.wz + dj2 * ttz;
         d.px = d.px + dt * d.vx;                                                     // :862
         d.py = d.py + dt * d.vy;
         d.pz = d.pz + dt * d.vz;
