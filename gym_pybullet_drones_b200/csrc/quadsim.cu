@@ -37,7 +37,10 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 constexpr int kMaxTPB = 128;          // threads (= drones) per CTA upper bound
 // fixed part of the step kernel's dynamic shared memory (heads, actions, reductions, in-CTA downwash positions, flags,
 // mbarrier), rounded so that the staged rows that follow are 128-byte aligned
-constexpr size_t kStepSmemFixed = ((size_t)kMaxTPB * 20 * 4 + (size_t)kMaxTPB * 4 * 4 + (size_t)kMaxTPB * 2 * 8 + (size_t)kMaxTPB * 3 * 8 + 3 * (size_t)kMaxTPB + 16 + 127) / 128 * 128;
+__host__ __device__ constexpr size_t smem_fixed(int cap) {
+    return ((size_t)cap * 20 * 4 + (size_t)cap * 4 * 4 + (size_t)cap * 2 * 8 + (size_t)cap * 3 * 8 + 3 * (size_t)cap + 16 + 127) / 128 * 128;
+}
+constexpr size_t kStepSmemFixed = smem_fixed(kMaxTPB);      // upper bound (cap = 128)
 
 struct StepArgs {
     QsParams P;
@@ -46,7 +49,7 @@ struct StepArgs {
     int act_type, task, n_envs, D, substeps, N, A, obs_dim, tpb, counter_inc;
     unsigned effects, flags;
     int stage_rows;      // 1: the CTA's prev_obs rows are staged in shared memory by one TMA bulk copy
-    int pad_;
+    int cap;             // CTA capacity in drones (64 or 128): sizes the shared-memory arrays
 };
 
 __device__ __forceinline__ float4 ldg4(const float* base, long long idx4) {
@@ -197,14 +200,16 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
     const int head = RAW ? 20 : 12;                            // floats staged per row
     // shared layout
     float* head_s = reinterpret_cast<float*>(smem_raw);                  // [tpb][head]
-    float* act_s = head_s + (size_t)kMaxTPB * 20;                        // [tpb][4]
-    double* red_s = reinterpret_cast<double*>(act_s + (size_t)kMaxTPB * 4);   // [tpb][2] reward, dist
-    double* pos_s = red_s + (size_t)kMaxTPB * 2;                         // [tpb][3] (in-CTA downwash)
-    unsigned char* oob_s = reinterpret_cast<unsigned char*>(pos_s + (size_t)kMaxTPB * 3);   // [tpb]
-    unsigned char* mode_s = oob_s + kMaxTPB;                             // [tpb] row mode: 0 shift, 1 keep history, 2 also final_obs
-    unsigned char* done_s = mode_s + kMaxTPB;                            // [tpb] per local env
-    unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(smem_raw + kStepSmemFixed - 16);   // mbarrier of the row staging
-    float* stage_s = reinterpret_cast<float*>(smem_raw + kStepSmemFixed);                                // [tpb][obs_dim] (+A) when staged
+    const int cap = a.cap;
+    const size_t fixed = smem_fixed(cap);
+    float* act_s = head_s + (size_t)cap * 20;                            // [tpb][4]
+    double* red_s = reinterpret_cast<double*>(act_s + (size_t)cap * 4);  // [tpb][2] reward, dist
+    double* pos_s = red_s + (size_t)cap * 2;                             // [tpb][3] (in-CTA downwash)
+    unsigned char* oob_s = reinterpret_cast<unsigned char*>(pos_s + (size_t)cap * 3);   // [tpb]
+    unsigned char* mode_s = oob_s + cap;                                 // [tpb] row mode: 0 shift, 1 keep history, 2 also final_obs
+    unsigned char* done_s = mode_s + cap;                                // [tpb] per local env
+    unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(smem_raw + fixed - 16);   // mbarrier of the row staging
+    float* stage_s = reinterpret_cast<float*>(smem_raw + fixed);                                // [tpb][obs_dim] (+A) when staged
 
     const long long e = live ? i / D : 0;
     const int le = t / D;                                      // local env (meaningful when D <= tpb)
@@ -502,7 +507,7 @@ struct RolloutArgs {
     QsRolloutIO io;
     int act_type, task, n_envs, D, substeps, N, A, obs_dim, tpb;
     unsigned effects, flags;
-    int stage_mode, pad_;
+    int stage_mode, cap;
 };
 
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
@@ -538,11 +543,13 @@ __global__ void __launch_bounds__(kMaxTPB, 4) rollout_kernel(const __grid_consta
     const bool live = (t < tpb) && (i < N);
     const int rows = (int)((N - c0) < tpb ? (N - c0) : tpb);
     double* red_s = reinterpret_cast<double*>(smem_raw);                               // [tpb][2]
-    double* pos_s = red_s + (size_t)kMaxTPB * 2;                                       // [tpb][3]
-    unsigned char* oob_s = reinterpret_cast<unsigned char*>(pos_s + (size_t)kMaxTPB * 3);
-    unsigned char* done_s = oob_s + kMaxTPB;
-    unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(smem_raw + kStepSmemFixed - 16);
-    float* stage_s = reinterpret_cast<float*>(smem_raw + kStepSmemFixed);              // [tpb*od + (T+1)*A] sliding window
+    const int cap = a.cap;
+    const size_t fixed = smem_fixed(cap);
+    double* pos_s = red_s + (size_t)cap * 2;                                           // [tpb][3]
+    unsigned char* oob_s = reinterpret_cast<unsigned char*>(pos_s + (size_t)cap * 3);
+    unsigned char* done_s = oob_s + cap;
+    unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(smem_raw + fixed - 16);
+    float* stage_s = reinterpret_cast<float*>(smem_raw + fixed);                       // [tpb*od + (T+1)*A] sliding window
 
     const long long e = live ? i / D : 0;
     const int le = t / D;
@@ -890,7 +897,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const long lon
 }
 
 size_t step_smem_bytes(const StepArgs& a) {
-    return kStepSmemFixed + (a.stage_rows ? (size_t)a.tpb * a.obs_dim * 4 + 32 : 0);
+    return smem_fixed(a.cap) + (a.stage_rows ? (size_t)a.tpb * a.obs_dim * 4 + 32 : 0);
 }
 
 template <bool RAW, bool PIDACT>
@@ -935,7 +942,25 @@ int check_state(const QsState* st, int need_tables) {
     return 0;
 }
 
-int block_size_for(int D) { return D <= kMaxTPB ? D * (kMaxTPB / D) : kMaxTPB; }
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// CTA capacity: 128 drones normally; 64 when 128-drone CTAs would not even fill two resident waves (4 CTAs per SM) --
+// e.g. 65 536 drones = 512 CTAs on 148 SMs leaves 68 SMs with 4 CTAs and 80 with 3 (15 % imbalance in a one-wave
+// kernel), whereas 1024 half-size CTAs spread 7/6 per SM (1 %).
+int cta_capacity(long long N, int D) {
+    if (D > 64) return kMaxTPB;
+    const long long ctas128 = (N + kMaxTPB - 1) / kMaxTPB;
+    return ctas128 < 8LL * sm_count() ? 64 : kMaxTPB;
+}
+
+int block_size_for(int D, int cap = kMaxTPB) { return D <= cap ? D * (cap / D) : cap; }
 
 }  // namespace
 
@@ -984,7 +1009,8 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
     a.P = *p; a.st = *st; a.io = *io;
     a.act_type = act_type; a.task = task; a.n_envs = n_envs; a.D = drones_per_env; a.substeps = substeps;
     a.N = n_envs * drones_per_env; a.A = A; a.obs_dim = state20 ? 20 : 12 + io->act_buffer_size * A;
-    a.tpb = block_size_for(drones_per_env);
+    a.cap = cta_capacity(a.N, drones_per_env);
+    a.tpb = block_size_for(drones_per_env, a.cap);
     a.counter_inc = io->tick_substeps > 0 ? io->tick_substeps : substeps;
     a.effects = effects; a.flags = flags;
     // staging of the CTA's prev_obs rows in shared memory: TMA bulk copy when every CTA's span is 16-byte aligned and sized,
@@ -1039,7 +1065,8 @@ int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int 
     a.P = *p; a.st = *st; a.io = *io;
     a.act_type = act_type; a.task = task; a.n_envs = n_envs; a.D = drones_per_env; a.substeps = substeps;
     a.N = n_envs * drones_per_env; a.A = A; a.obs_dim = 12 + io->act_buffer_size * A;
-    a.tpb = block_size_for(drones_per_env);
+    a.cap = cta_capacity(a.N, drones_per_env);
+    a.tpb = block_size_for(drones_per_env, a.cap);
     a.effects = effects; a.flags = flags;
     {
         const size_t row_bytes = (size_t)a.obs_dim * 4, span = row_bytes * a.tpb;
@@ -1048,7 +1075,7 @@ int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int 
     }
     const int blocks = (int)((a.N + a.tpb - 1) / a.tpb);
     const int threads = ((a.tpb + 31) / 32) * 32;
-    const size_t sm = kStepSmemFixed + (size_t)a.tpb * a.obs_dim * 4 + (size_t)(io->T + 1) * A * 4 + 32;
+    const size_t sm = smem_fixed(a.cap) + (size_t)a.tpb * a.obs_dim * 4 + (size_t)(io->T + 1) * A * 4 + 32;
     cudaStream_t s = (cudaStream_t)stream;
 #define QS_RCASE(E)                                                                                                   \
     case E: {                                                                                                         \
@@ -1146,7 +1173,8 @@ int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, floa
     a.io.action = rpm; a.io.obs = state20_out; a.io.dw_fz = dw_fz;
     a.act_type = QS_ACT_RAW_RPM; a.task = QS_TASK_NONE; a.n_envs = n_envs; a.D = drones_per_env; a.substeps = substeps;
     a.N = n_envs * drones_per_env; a.A = 4; a.obs_dim = 20;
-    a.tpb = block_size_for(drones_per_env);
+    a.cap = cta_capacity(a.N, drones_per_env);
+    a.tpb = block_size_for(drones_per_env, a.cap);
     a.counter_inc = substeps;
     a.effects = effects; a.flags = flags & QS_FLAG_RPY_F32;
     const cudaError_t e = launch_step<true, false>(a, (cudaStream_t)stream);
