@@ -942,22 +942,16 @@ int check_state(const QsState* st, int need_tables) {
     return 0;
 }
 
-int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
-
-// CTA capacity: 128 drones normally; 64 when 128-drone CTAs would not even fill two resident waves (4 CTAs per SM) --
-// e.g. 65 536 drones = 512 CTAs on 148 SMs leaves 68 SMs with 4 CTAs and 80 with 3 (15 % imbalance in a one-wave
-// kernel), whereas 1024 half-size CTAs spread 7/6 per SM (1 %).
-int cta_capacity(long long N, int D) {
-    if (D > 64) return kMaxTPB;
-    const long long ctas128 = (N + kMaxTPB - 1) / kMaxTPB;
-    return ctas128 < 8LL * sm_count() ? 64 : kMaxTPB;
+// CTA capacity in drones.  Measured on B200 (tools/ab.py, same box): 32-drone CTAs (one warp) beat 64 and 128 for the
+// single-tick kernels at every size (65 536 drones: 16.2 / 16.1 / 17.3 us, 1 M drones: 161 / 162 / 169 us) -- more,
+// smaller CTAs per SM sit at different phases (load / FP64 / store) at any instant, and 65 536 drones spread 14/13 per
+// SM instead of 4/3.  The multi-tick rollout keeps its window in shared memory for many ticks and prefers 64.
+int cta_capacity(long long N, int D, bool rollout = false) {
+    static const int forced = getenv("QS_CTA_CAP") ? atoi(getenv("QS_CTA_CAP")) : 0;      // experiments only
+    if (forced == 32 || forced == 64 || forced == 128) return D <= forced ? forced : kMaxTPB;
+    (void)N;
+    if (D <= 32 && !rollout) return 32;
+    return D <= 64 ? 64 : kMaxTPB;
 }
 
 int block_size_for(int D, int cap = kMaxTPB) { return D <= cap ? D * (cap / D) : cap; }
@@ -1065,7 +1059,7 @@ int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int 
     a.P = *p; a.st = *st; a.io = *io;
     a.act_type = act_type; a.task = task; a.n_envs = n_envs; a.D = drones_per_env; a.substeps = substeps;
     a.N = n_envs * drones_per_env; a.A = A; a.obs_dim = 12 + io->act_buffer_size * A;
-    a.cap = cta_capacity(a.N, drones_per_env);
+    a.cap = cta_capacity(a.N, drones_per_env, true);
     a.tpb = block_size_for(drones_per_env, a.cap);
     a.effects = effects; a.flags = flags;
     {
