@@ -312,16 +312,13 @@ QS_HD void pid_control(const QsParams& P, PidState& st, double dt,
     const double xx = yy * zz - yz * zy, xy = yz * zx - yx * zz, xz = yx * zy - yy * zx;   // y x z (:202)
     // target_rotation columns = [x_ax y_ax z_ax] (:203): Rd[r][c]
     const double Rd[9] = {xx, yx, zx, xy, yy, zy, xz, yz, zz};
-    // scipy as_euler('XYZ') of Rd (:205), intrinsic XYZ: Rd = Rx(a) Ry(b) Rz(c)
-    const double ea = atan2(-Rd[5], Rd[8]);
-    const double eb = asin(clampd(Rd[2], -1.0, 1.0));
+    // The reference converts Rd to intrinsic-XYZ Euler angles (scipy as_euler('XYZ'), :205) and, in the attitude loop,
+    // straight back to a matrix (from_euler('XYZ').as_quat() -> from_quat().as_matrix(), :242-244).  That round trip is
+    // the identity on rotation matrices (also in gimbal lock, where only the angle split is ambiguous), so the target
+    // rotation used below IS Rd; of the three angles only c = atan2(-Rd[0][1], Rd[0][0]) is ever consumed (yaw error, :145).
     const double ec = atan2(-Rd[1], Rd[0]);
     pos_e[0] = ex; pos_e[1] = ey; pos_e[2] = ez;
-    // attitude loop (:240-259): target_rotation rebuilt from target_euler (from_euler('XYZ').as_matrix())
-    const double ca = cos(ea), sa = sin(ea), cb = cos(eb), sb = sin(eb), cc = cos(ec), sc = sin(ec);
-    const double T[9] = {cb * cc, -cb * sc, sb,
-                         ca * sc + sa * sb * cc, ca * cc - sa * sb * sc, -sa * cb,
-                         sa * sc - ca * sb * cc, sa * cc + ca * sb * sc, ca * cb};
+    const double* T = Rd;
     double roll, pitch, yaw;
     quat_to_euler<false>(qx, qy, qz, qw, roll, pitch, yaw);                          // :241
     // E = T^T R - R^T T ; rot_e = (E[2][1], E[0][2], E[1][0])  (:245-246)
