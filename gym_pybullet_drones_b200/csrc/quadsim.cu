@@ -216,6 +216,11 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
     const int dslot = (int)(i - e * D);                        // drone index inside its aviary
     const long long tbl = a.st.tables_per_env ? i : dslot;
 
+    // Programmatic dependent launch: when the host launched this grid with programmatic stream serialization its CTAs
+    // may already be resident while the previous kernel in the stream drains; nothing written by that kernel is read
+    // before this point (no-op for ordinary launches).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     qs::Drone d;
     qs::Derived o;
     qs::PidState pst = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -415,6 +420,8 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
             }
         }
     }
+    // all the FP64 work of this CTA is done: let the next grid in the stream start moving in behind the stores
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (a.io.obs == nullptr || !want_epilogue) return;
     const int od = a.obs_dim;
     if (want_rows && a.stage_rows) {
@@ -905,6 +912,13 @@ cudaError_t launch_step(const StepArgs& a, cudaStream_t s) {
     const int blocks = (int)((a.N + a.tpb - 1) / a.tpb);
     const int threads = ((a.tpb + 31) / 32) * 32;
     const size_t sm = step_smem_bytes(a);
+    static const bool pdl = !(getenv("QS_PDL") && atoi(getenv("QS_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = sm; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
 #define QS_CASE(E)                                                                                               \
     case E: {                                                                                                    \
         static bool attr_set = false;                                                                            \
@@ -913,8 +927,8 @@ cudaError_t launch_step(const StepArgs& a, cudaStream_t s) {
                                  (int)(kStepSmemFixed + kStageLimit + 32));                                           \
             attr_set = true;                                                                                     \
         }                                                                                                        \
-        step_kernel<E, RAW, PIDACT><<<blocks, threads, sm, s>>>(a);                                              \
-    } break;
+        return cudaLaunchKernelEx(&cfg, step_kernel<E, RAW, PIDACT>, a);                                         \
+    }
     switch (a.effects & 7u) {
         QS_CASE(0) QS_CASE(1) QS_CASE(2) QS_CASE(3) QS_CASE(4) QS_CASE(5) QS_CASE(6) QS_CASE(7)
     }
