@@ -486,8 +486,12 @@ class BaseAviary(Env):
                 return self._shape_obs(obs), self._reward, self._terminated, self._truncated, info
             #### NumPy path: pinned H2D of the action, D2H of the results, all inside this call ####
             a_np = np.asarray(action, dtype=np.float32).reshape(self._N, self._A)
-            if self.VECTORIZED and self._simple_launch:
-                return self._step_host(a_np)
+            if self._simple_launch:
+                o, rew, term, trunc, info = self._step_host(a_np)
+                if self.VECTORIZED:
+                    return o, rew, term, trunc, info
+                # single-env API of the reference: (obs[D, .], float, bool, bool, info)  (BaseAviary.py:376-383)
+                return o[0], float(rew[0]), bool(term[0]), bool(trunc[0]), self._computeInfo()
             self._h_action.numpy()[...] = a_np
             self._action_dev.copy_(self._h_action, non_blocking=True)
             obs = self._launch(self._action_dev)

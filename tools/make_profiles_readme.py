@@ -58,6 +58,26 @@ if cfg:
                                                                    ("%.3f" % v["hbm_frac"]) if "hbm_frac" in v else ("%.3g pairs/s" % v["pairs_per_s"] if "pairs_per_s" in v else "-"), v.get("note", "")))
         else:
             L.append("| %s | n=%s | - | %.4f | %.3g calls/s | %s | %.3f | |" % (k, v["n"], v["ms_per_call"], v["calls_per_s"], v["alg_bytes"], v["hbm_frac"]))
+L.append("""
+## Optimisation log of the step kernel (65 536 drones, S=8, A=4, B=15; `bench.py` `ms_per_step`, each measured on a B200 via gpurun)
+
+| commit milestone | us / step | what changed (evidence) |
+|---|---|---|
+| first parity-green kernel | 102.6 | one LDG->STG round trip per observation row (`r01_a_first_correct_kernel_ncu.md`: stall_long_sb on the row copy) |
+| L2 bulk prefetch + 8-deep unrolled float4 row copies | 38.8 | `cp.async.bulk.prefetch.L2` of the CTA's history span |
+| division-free FP64 tick, rpy in f32 | 31.6 | 2/|q|^2 -> 2(2-|q|^2), 1/M hoisted; 12.3k -> 7.6k instructions per warp |
+| TMA bulk copy of the span into shared memory behind the physics | 24.2 | `UBLKCP.S.G` + mbarrier; Python fast path (host 13.8 -> 8.5 us per call) |
+| flat shifted-span writer (rows patched in shared memory) | 21.6 | 3.8k -> 2.2k instructions per warp |
+| state loads ahead of the bulk copy, LDS (not generic LD) copy-out | 18.7 | `r01_f_step_kernel_ncu.md` |
+| 5-term series below 42 rad/s, fused Euler constants, diagonal-J gyro term | 17.7 | 835 -> ~640 FP64 instructions per tick (A/B on one box: 18.1 -> 17.7) |
+| 64-drone, then one-warp (32-drone) CTAs | 16.2 | A/B on one box: 32/64/128-drone CTAs = 16.2/16.1/17.3 us; 1 M drones 161/162/169 us |
+| programmatic dependent launch (griddepcontrol) | 14.3 | A/B on one box: 16.24 -> 14.20 us |
+
+Tried and rejected (measured): issuing the TMA copy before the state loads (ncu 16.1 vs 14.8 us); writing the history
+columns out before the physics to overlap stores with FP64 work (22.1 vs 18.7 us: the physics then waits for the bulk
+copy).  Box-to-box spread of the same binary is up to ~10 % at 1 M drones (158-176 us), so only same-box A/B numbers are
+compared.
+""")
 L.append("\n## ncu captures (`ncu --set full --clock-control none --import-source on`, one GPU, `bench.py --steps 20`)\n")
 for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_*_ncu.md"))):
     L.append("* `%s` — %s" % (os.path.basename(f), open(f).read().split("\n")[2]))
