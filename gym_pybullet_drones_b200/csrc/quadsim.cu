@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
         }
         __syncthreads();
         const bool clear_hist = a.flags & QS_FLAG_AUTORESET_CLEARS_HISTORY;
-        const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+        const int lane = t & 31;
         if (A == 4) {
             const float4* src = reinterpret_cast<const float4*>(stage_s) + 1;
             float4* out = reinterpret_cast<float4*>(a.io.obs + c0 * od);
@@ -462,12 +462,16 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
                 out[j] = v0; out[j + nt] = v1; out[j + 2 * nt] = v2; out[j + 3 * nt] = v3; out[j + 4 * nt] = v4; out[j + 5 * nt] = v5;
             }
             for (; j < n4; j += nt) out[j] = src[j];
-            // SAME_STEP autoreset: the history part of the terminal observation of finished rows, one warp per row
+            // SAME_STEP autoreset: the history part of the terminal observation of finished rows.  Each warp ballots the
+            // flags of its own 32 rows and copies only the flagged ones, a whole row per instruction.
             if (a.io.final_obs && (a.flags & QS_FLAG_AUTORESET_SAME_STEP)) {
                 float4* fin = reinterpret_cast<float4*>(a.io.final_obs + c0 * od);
-                for (int r = warp; r < rows; r += nwarps)
-                    if (mode_s[r] & 2)
-                        for (int c = 3 + lane; c < c4n; c += 32) fin[r * c4n + c] = src[r * c4n + c];
+                unsigned m = __ballot_sync(0xffffffffu, live && (mode_s[t] & 2));
+                const int r0 = t & ~31;
+                for (; m; m &= m - 1) {
+                    const int r = r0 + __ffs(m) - 1;
+                    for (int c = 3 + lane; c < c4n; c += 32) fin[r * c4n + c] = src[r * c4n + c];
+                }
             }
         } else {
             const float* src = stage_s + A;
@@ -475,9 +479,12 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
             for (int j = t; j < rows * od; j += blockDim.x) out[j] = src[j];
             if (a.io.final_obs && (a.flags & QS_FLAG_AUTORESET_SAME_STEP)) {
                 float* fin = a.io.final_obs + c0 * od;
-                for (int r = warp; r < rows; r += nwarps)
-                    if (mode_s[r] & 2)
-                        for (int c = 12 + lane; c < od; c += 32) fin[r * od + c] = src[r * od + c];
+                unsigned m = __ballot_sync(0xffffffffu, live && (mode_s[t] & 2));
+                const int r0 = t & ~31;
+                for (; m; m &= m - 1) {
+                    const int r = r0 + __ffs(m) - 1;
+                    for (int c = 12 + lane; c < od; c += 32) fin[r * od + c] = src[r * od + c];
+                }
             }
         }
         if (clear_hist) {                                     // optional: the observation after a reset carries an empty action buffer
