@@ -455,13 +455,25 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
             const float4* src = reinterpret_cast<const float4*>(stage_s) + 1;
             float4* out = reinterpret_cast<float4*>(a.io.obs + c0 * od);
             const int c4n = od >> 2, n4 = rows * c4n;
-            const int nt = blockDim.x;
-            int j = t;
-            for (; j + 5 * nt < n4; j += 6 * nt) {            // 6 independent LDS.128 in flight, then 6 coalesced STG.128
-                const float4 v0 = src[j], v1 = src[j + nt], v2 = src[j + 2 * nt], v3 = src[j + 3 * nt], v4 = src[j + 4 * nt], v5 = src[j + 5 * nt];
-                out[j] = v0; out[j + nt] = v1; out[j + 2 * nt] = v2; out[j + 3 * nt] = v3; out[j + 4 * nt] = v4; out[j + 5 * nt] = v5;
+            if (a.stage_rows == 1) {
+                // TMA bulk store: one thread hands the whole patched span (shared memory, shifted by one action) to the
+                // copy engine; the other threads go on to the terminal-observation rows.  The async proxy must see the
+                // generic-proxy patches (fence), and shared memory must stay alive until it has been read (wait_group.read).
+                if (t == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(out), "r"(smem_u32(src)), "r"((unsigned)(n4 * 16)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else {
+                const int nt = blockDim.x;
+                int j = t;
+                for (; j + 5 * nt < n4; j += 6 * nt) {        // 6 independent LDS.128 in flight, then 6 coalesced STG.128
+                    const float4 v0 = src[j], v1 = src[j + nt], v2 = src[j + 2 * nt], v3 = src[j + 3 * nt], v4 = src[j + 4 * nt], v5 = src[j + 5 * nt];
+                    out[j] = v0; out[j + nt] = v1; out[j + 2 * nt] = v2; out[j + 3 * nt] = v3; out[j + 4 * nt] = v4; out[j + 5 * nt] = v5;
+                }
+                for (; j < n4; j += nt) out[j] = src[j];
             }
-            for (; j < n4; j += nt) out[j] = src[j];
             // SAME_STEP autoreset: the history part of the terminal observation of finished rows.  Each warp ballots the
             // flags of its own 32 rows and copies only the flagged ones, a whole row per instruction.
             if (a.io.final_obs && (a.flags & QS_FLAG_AUTORESET_SAME_STEP)) {
@@ -486,6 +498,10 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
                     for (int c = 12 + lane; c < od; c += 32) fin[r * od + c] = src[r * od + c];
                 }
             }
+        }
+        if (A == 4 && a.stage_rows == 1 && t == 0) {
+            if (clear_hist) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // stores complete (ordering vs the zeroing below)
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");             // shared memory has been read
         }
         if (clear_hist) {                                     // optional: the observation after a reset carries an empty action buffer
             __syncthreads();

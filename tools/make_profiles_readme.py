@@ -81,7 +81,22 @@ compared.
 L.append("\n## ncu captures (`ncu --set full --clock-control none --import-source on`, one GPU, `bench.py --steps 20`)\n")
 for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_*_ncu.md"))):
     L.append("* `%s` — %s" % (os.path.basename(f), open(f).read().split("\n")[2]))
-L.append("* `r01_a_launches.csv` — `ncu --metrics gpu__time_duration.sum` launch list of the first correct kernel (one `step_kernel` launch per env.step; the only other launches are torch fills/copies at setup).")
+L.append("* `r01_a_launches.csv` — launch list of the first correct kernel (setup part only).")
+try:
+    import collections, csv
+    rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r01_z_launches_final.csv"))) if len(r) > 14 and r[0].isdigit()]
+    cnt, tot = collections.Counter(), collections.Counter()
+    for r in rows:
+        name = r[4].split("(")[0].replace("void ", "").replace("<unnamed>::", "")[-60:]
+        cnt[name] += 1
+        tot[name] += float(r[-1])
+    allt = sum(tot.values())
+    L.append("* `r01_z_launches_final.csv` — `ncu --metrics gpu__time_duration.sum --clock-control none` over a whole `bench.py --steps 40` run (%d launches; cold-cache, serialised: shares, not absolutes):\n" % len(rows))
+    L.append("  | kernel | launches | share of GPU time |\n  |---|---|---|")
+    for k, v in tot.most_common(6):
+        L.append("  | `%s` | %d | %.1f %% |" % (k, cnt[k], 100 * v / allt))
+except Exception as ex:
+    L.append("* launch list: %r" % (ex,))
 L.append("\n`traffic` in the bench JSON: ncu's `dram__bytes_read.sum` is 24.3 MB per launch (state 4.2 MB + actions 1 MB + old observation span 18.9 MB = the algorithmic reads); `dram__bytes_write.sum` reads ~0 inside the kernel because the 23 MB of stores are still in the 126 MB write-back L2 when the kernel ends.")
 open(os.path.join(ROOT, "profiles", "README.md"), "w").write("\n".join(L) + "\n")
 print("\n".join(L))
