@@ -308,13 +308,16 @@ def main():
         extras["cuda_graph_replay"] = {"error": repr(ex)}
     if "ms_per_step" in extras.get("cuda_graph_replay", {}):
         gms = extras["cuda_graph_replay"]["ms_per_step"]
+        timing = "CUDA events around K back-to-back graph-captured launches / K"
+        if ms / a.steps < gms:      # the plain timed loop (PDL launches, also back to back) bounds the kernel duration as well
+            gms, timing = ms / a.steps, "CUDA events around the K back-to-back launches of the timed region / K"
         if gms < roofline["kernel_ms"]:
             # back-to-back launches of ONLY this kernel inside one CUDA graph: elapsed/K bounds the kernel duration from
             # above without the ~3 us of event/launch gap that per-launch event pairs include
             roofline.update(kernel_ms_event_pairs=roofline["kernel_ms"], kernel_ms=gms,
                             achieved=ALG_BYTES * DRONES_PER_GPU / (gms * 1e-3) / 1e9,
                             frac=ALG_BYTES * DRONES_PER_GPU / (gms * 1e-3) / 1e9 / peak_gbs,
-                            timing="CUDA events around K back-to-back graph-captured launches / K")
+                            timing=timing)
     # the same kernel at sizes where several waves overlap load, compute and store (one batch, working set > L2)
     sweep = {}
     if world == 1:

@@ -735,7 +735,18 @@ __global__ void __launch_bounds__(kMaxTPB, 4) rollout_kernel(const __grid_consta
         {
             float* outp = a.io.obs + ((long long)k * N + c0) * od;
             float* lastp = (k == T - 1 && a.io.obs_last) ? a.io.obs_last + c0 * od : nullptr;
-            if (A == 4) {
+            if (A == 4 && a.stage_mode == 1) {
+                // TMA bulk store of the window (see step_kernel); the window is rewritten next tick, so wait until the
+                // copy engine has read it
+                if (t == 0) {
+                    const unsigned bytes = (unsigned)(rows * od * 4);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(outp), "r"(smem_u32(base)), "r"(bytes) : "memory");
+                    if (lastp) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(lastp), "r"(smem_u32(base)), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+            } else if (A == 4) {
                 const float4* src = reinterpret_cast<const float4*>(base);
                 float4* out = reinterpret_cast<float4*>(outp);
                 float4* last = reinterpret_cast<float4*>(lastp);
