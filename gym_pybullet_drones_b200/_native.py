@@ -77,8 +77,14 @@ class QsHostIO(C.Structure):
                                           "final_obs_host", "final_env_host", "n_final_host", "action_dev", "final_env_dev", "final_rows_dev")]
 
 
+class QsStepCall(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("st", C.c_void_p), ("io", C.c_void_p),
+                ("act_type", C.c_int), ("task", C.c_int), ("n_envs", C.c_int), ("drones_per_env", C.c_int), ("substeps", C.c_int),
+                ("effects", C.c_uint), ("flags", C.c_uint), ("pad_", C.c_int)]
+
+
 EXPORTS = ["qs_abi_version", "qs_last_error", "qs_sizeof_params", "qs_sizeof_state", "qs_sizeof_step_io",
-           "qs_sizeof_rollout_io", "qs_sizeof_host_io", "qs_step", "qs_step_host", "qs_rollout", "qs_rollout_max_ticks", "qs_dyn_substeps", "qs_pid_control",
+           "qs_sizeof_rollout_io", "qs_sizeof_host_io", "qs_step", "qs_step_call", "qs_step_host", "qs_rollout", "qs_rollout_max_ticks", "qs_dyn_substeps", "qs_pid_control",
            "qs_downwash", "qs_reset"]
 
 
@@ -118,6 +124,8 @@ def lib():
     L.qs_step.restype = C.c_int
     L.qs_step.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.POINTER(QsStepIO), C.c_int, C.c_int,
                           C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
+    L.qs_step_call.restype = C.c_int
+    L.qs_step_call.argtypes = [C.c_void_p, C.c_void_p]
     L.qs_step_host.restype = C.c_int
     L.qs_step_host.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.POINTER(QsStepIO), C.POINTER(QsHostIO), C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]

@@ -1138,6 +1138,11 @@ int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int 
 
 int qs_sizeof_host_io(void) { return (int)sizeof(QsHostIO); }
 
+int qs_step_call(const QsStepCall* c, void* stream) {
+    if (!c) return fail(QS_ERR_NULL, "qs_step_call: NULL call");
+    return qs_step(c->p, c->st, c->io, c->act_type, c->task, c->n_envs, c->drones_per_env, c->substeps, c->effects, c->flags, stream);
+}
+
 int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const QsHostIO* h, int act_type, int task,
                  int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream) {
     if (!io || !h) return fail(QS_ERR_NULL, "qs_step_host: NULL io");

@@ -264,6 +264,12 @@ class BaseAviary(Env):
         self._step_head = (C.byref(self._P), C.byref(self._st), C.byref(io), self._act_type(), self._task(),
                            E, D, self.PYB_STEPS_PER_CTRL, self._effects, self._flags)
         self._dev_index = self.device.index
+        call = N.QsStepCall()
+        call.p, call.st, call.io = C.addressof(self._P), C.addressof(self._st), C.addressof(io)
+        call.act_type, call.task, call.n_envs, call.drones_per_env = self._act_type(), self._task(), E, D
+        call.substeps, call.effects, call.flags = self.PYB_STEPS_PER_CTRL, self._effects, self._flags
+        self._call, self._call_ptr, self._qs_step_call = call, C.addressof(call), self._lib.qs_step_call
+        self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
         #### pinned host staging for the NumPy API ####
         self._h_action = torch.zeros((n, self._A), dtype=torch.float32).pin_memory()
         self._h_obs = [torch.zeros((n, self._obs_dim), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -460,7 +466,8 @@ class BaseAviary(Env):
             io.action = a.data_ptr()
             io.obs_prev = self._obs_ptr[cur]
             io.obs = self._obs_ptr[1 - cur]
-            rc = self._qs_step(*self._step_head, torch.cuda.current_stream().cuda_stream)
+            stream = self._raw_stream(self._dev_index) if self._raw_stream else torch.cuda.current_stream().cuda_stream
+            rc = self._qs_step_call(self._call_ptr, stream)
             if rc:
                 N.check(rc, "qs_step")
             self._cur = cur = 1 - cur

@@ -197,6 +197,15 @@ int qs_sizeof_host_io(void);
 int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_type, int task,
             int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream);
 
+/* qs_step with all arguments in one caller-owned struct (a hot loop then passes two pointers per tick). */
+typedef struct QsStepCall {
+    const QsParams* p; const QsState* st; const QsStepIO* io;
+    int act_type, task, n_envs, drones_per_env, substeps;
+    unsigned effects, flags;
+    int pad_;
+} QsStepCall;
+int qs_step_call(const QsStepCall* c, void* stream);
+
 /* qs_step with host buffers: H2D(action) -> fused tick -> D2H(reward, flags) -> D2H(obs) (+ a compact D2H of the terminal
  * observations of finished aviaries).  `io` carries the device buffers exactly as for qs_step (io->action is ignored).
  * Unlike every other entry point this one SYNCHRONISES `stream` before returning (the host arrays are valid on return). */

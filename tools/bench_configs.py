@@ -71,6 +71,30 @@ out["config3_multihover_one_d_rpm_65536"] = {"drones": E * D, "S": 8, "ms_per_st
                                              "hbm_frac": 286 * E * D / (ms * 1e-3) / 1e9 / PEAK}
 del envs
 
+# config 3 (ii): SB3-MlpPolicy-shaped torch network + env entirely on the device, captured in a CUDA graph
+E, D = 32768, 2
+env = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E, autoreset="same_step")
+torch.manual_seed(0)
+pi = torch.nn.Sequential(torch.nn.Linear(D * 72, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(), torch.nn.Linear(64, D * 4)).cuda()
+obs, _ = env.reset()
+act = torch.zeros((E, D, 4), device=dev)
+def pol_step(o):
+    with torch.no_grad():
+        mean = pi(o.reshape(E, -1))
+        act.copy_((mean + 0.3 * torch.randn_like(mean)).clamp(-1, 1).view(E, D, 4))
+    return env.step(act)[0]
+for _ in range(4):
+    obs = pol_step(obs)
+torch.cuda.synchronize()
+gr = torch.cuda.CUDAGraph()
+views = [env._obs_view[0], env._obs_view[1]]
+with torch.cuda.graph(gr):
+    pol_step(views[env._cur]); pol_step(views[env._cur])
+ms = timed(gr.replay, 200, 10) / 2
+out["config3_policy_plus_env_cuda_graph_65536"] = {"drones": E * D, "S": 8, "ms_per_step": ms, "drone_steps_per_s": E * D / (ms * 1e-3),
+                                                   "note": "fp32 MLP 144-64-64-8 (tanh) with Gaussian exploration noise + fused env step, 2 steps per graph replay"}
+del env, gr
+
 # S=1: 240 Hz control, B=120
 E, D = 32768, 2
 env = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, pyb_freq=240, ctrl_freq=240, num_envs=E, autoreset="same_step")

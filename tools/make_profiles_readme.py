@@ -72,10 +72,13 @@ L.append("""
 | 5-term series below 42 rad/s, fused Euler constants, diagonal-J gyro term | 17.7 | 835 -> ~640 FP64 instructions per tick (A/B on one box: 18.1 -> 17.7) |
 | 64-drone, then one-warp (32-drone) CTAs | 16.2 | A/B on one box: 32/64/128-drone CTAs = 16.2/16.1/17.3 us; 1 M drones 161/162/169 us |
 | programmatic dependent launch (griddepcontrol) | 14.3 | A/B on one box: 16.24 -> 14.20 us |
+| terminal-observation rows by warp ballot instead of a serial flag scan | 13.1 | `LDS.U8 -> LOP3 -> BRA` chain was 25 % of the samples; 1 M drones 159 -> 143 us |
+| TMA bulk store (`cp.async.bulk` S2G, `UBLKCP.G.S`) of the observation span | 12.4 | A/B on one box: 13.08 -> 12.42 us; rollout 7.57 -> 7.21 us per tick |
 
 Tried and rejected (measured): issuing the TMA copy before the state loads (ncu 16.1 vs 14.8 us); writing the history
 columns out before the physics to overlap stores with FP64 work (22.1 vs 18.7 us: the physics then waits for the bulk
-copy).  Box-to-box spread of the same binary is up to ~10 % at 1 M drones (158-176 us), so only same-box A/B numbers are
+copy); trimming the step kernel's fixed shared memory so 18 instead of 15 CTAs fit per SM (12.44 -> 12.64 us at 65 536
+drones, 138.6 -> 136.0 us at 1 M: not adopted).  Box-to-box spread of the same binary is up to ~10 % at 1 M drones (158-176 us), so only same-box A/B numbers are
 compared.
 """)
 L.append("\n## ncu captures (`ncu --set full --clock-control none --import-source on`, one GPU, `bench.py --steps 20`)\n")
