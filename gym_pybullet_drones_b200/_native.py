@@ -85,7 +85,8 @@ class QsStepCall(C.Structure):
 
 EXPORTS = ["qs_abi_version", "qs_last_error", "qs_sizeof_params", "qs_sizeof_state", "qs_sizeof_step_io",
            "qs_sizeof_rollout_io", "qs_sizeof_host_io", "qs_step", "qs_step_call", "qs_step_host", "qs_rollout", "qs_rollout_max_ticks", "qs_dyn_substeps", "qs_pid_control",
-           "qs_downwash", "qs_reset"]
+           "qs_downwash", "qs_downwash_boxed", "qs_dw_gathered_floats", "qs_dw_boxes", "qs_downwash_rows", "qs_dw_publish", "qs_enable_peer_access", "qs_ipc_export", "qs_ipc_import", "qs_adjacency", "qs_reset"]
+MAX_PEERS = 16
 
 
 def build(force=False, verbose=False):
@@ -145,6 +146,26 @@ def lib():
                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.qs_downwash.restype = C.c_int
     L.qs_downwash.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.qs_downwash_boxed.restype = C.c_int
+    L.qs_downwash_boxed.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.qs_dw_gathered_floats.restype = C.c_longlong
+    L.qs_dw_gathered_floats.argtypes = [C.c_int]
+    L.qs_dw_boxes.restype = C.c_int
+    L.qs_dw_boxes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.qs_downwash_rows.restype = C.c_int
+    L.qs_downwash_rows.argtypes = [C.POINTER(QsParams), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    L.qs_dw_publish.restype = C.c_int
+    L.qs_dw_publish.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                C.c_uint, C.c_void_p, C.c_void_p]
+    L.qs_enable_peer_access.restype = C.c_int
+    L.qs_enable_peer_access.argtypes = [C.c_int]
+    L.qs_ipc_export.restype = C.c_int
+    L.qs_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_ulonglong)]
+    L.qs_ipc_import.restype = C.c_int
+    L.qs_ipc_import.argtypes = [C.c_void_p, C.c_ulonglong, C.POINTER(C.c_void_p)]
+    L.qs_adjacency.restype = C.c_int
+    L.qs_adjacency.argtypes = [C.POINTER(QsState), C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
     L.qs_reset.restype = C.c_int
     L.qs_reset.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.c_void_p, C.c_int, C.c_int,
                            C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

@@ -43,6 +43,7 @@ class BaseAviary(Env):
     """Base class for the GPU aviaries (reference: envs/BaseAviary.py:19)."""
 
     metadata = {"render_modes": []}
+    _EXTERNAL_DOWNWASH = False      # True: the downwash force always comes from `_downwash_stage` (sharded formations)
 
     ################################################################################
 
@@ -225,8 +226,9 @@ class BaseAviary(Env):
         self._truncated = torch.zeros((E,), dtype=torch.bool, device=dev)
         self._done = torch.zeros((E,), dtype=torch.bool, device=dev)
         self._final_obs = torch.zeros((n, self._obs_dim), **f32) if (self._flags & N.FLAG_AUTORESET_SAME_STEP) else None
-        big_dw = (self._effects & N.EFFECT_DW) and D > 128
+        big_dw = (self._effects & N.EFFECT_DW) and (D > 128 or self._EXTERNAL_DOWNWASH)
         self._dw_fz = torch.zeros((n,), **f32) if big_dw else None
+        self._dw_boxes = torch.zeros((E, (D + 31) // 32, 8), **f32) if big_dw else None     # chunk boxes (qs_downwash_boxed)
         self._action_dev = torch.zeros((n, self._A), **f32)
         #### tables ####
         if np.asarray(self.INIT_XYZS).ndim != np.asarray(self.INIT_RPYS).ndim and self._tables_per_env:
@@ -426,7 +428,7 @@ class BaseAviary(Env):
         else:
             # aviary larger than one CTA with downwash: positions couple the drones every substep
             for s in range(S):
-                N.check(L.qs_downwash(C.byref(self._P), C.byref(self._st), self._E, self._D, self._dw_fz.data_ptr(), stream), "qs_downwash")
+                self._downwash_stage(stream)
                 if raw:
                     last = s == S - 1
                     rpm_src = io.action if s == 0 else self._last_rpm.data_ptr()
@@ -440,6 +442,11 @@ class BaseAviary(Env):
                 N.check(rc, "qs_step(split)")
         self._cur = 1 - cur
         return self._obs_buf[self._cur]
+
+    def _downwash_stage(self, stream):
+        """Pairwise downwash force of the current positions into `_dw_fz` (BaseAviary.py:785-811), once per substep."""
+        N.check(self._lib.qs_downwash_boxed(C.byref(self._P), C.byref(self._st), self._E, self._D, self._dw_boxes.data_ptr(),
+                                            self._dw_fz.data_ptr(), stream), "qs_downwash_boxed")
 
     def _shape_obs(self, obs):
         return obs.view(self._E, self._D, self._obs_dim)
@@ -593,11 +600,19 @@ class BaseAviary(Env):
     def _getDroneStateVector(self, nth_drone):
         return self._getDroneStateVectors()[0, nth_drone]
 
+    def adjacency(self, out=None):
+        """Neighbourhood query for every aviary: uint8 tensor [E, D, D], 1 where i == j or the drones are closer
+        than NEIGHBOURHOOD_RADIUS (BaseAviary._getAdjacencyMatrix, BaseAviary.py:658-675)."""
+        if out is None:
+            out = torch.empty((self._E, self._D, self._D), dtype=torch.uint8, device=self.device)
+        with self._on_device():
+            N.check(self._lib.qs_adjacency(C.byref(self._st), self._E, self._D, float(self.NEIGHBOURHOOD_RADIUS),
+                                           out.data_ptr(), self._stream()), "qs_adjacency")
+        return out
+
     def _getAdjacencyMatrix(self):
-        """BaseAviary._getAdjacencyMatrix (BaseAviary.py:658-675) for the first aviary."""
-        p = self._planes[0, :self._D, 0:3].double()
-        d = torch.cdist(p, p)
-        return (d < self.NEIGHBOURHOOD_RADIUS).double().cpu().numpy()
+        """BaseAviary._getAdjacencyMatrix (BaseAviary.py:658-675) for the first aviary: float64 ndarray [D, D]."""
+        return self.adjacency()[0].cpu().numpy().astype(np.float64)
 
     ################################################################################
     # hooks (BaseAviary.py:1021-1104)

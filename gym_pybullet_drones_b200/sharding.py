@@ -41,20 +41,30 @@ def shard_envs(total_envs: int, rank: int = None, world: int = None) -> EnvShard
     return EnvShard(rank, world, total_envs, start, start + base + (1 if rank < extra else 0))
 
 
-def all_gather_envs(local: torch.Tensor, shard: EnvShard, group=None) -> torch.Tensor:
+def all_gather_envs(local: torch.Tensor, shard: EnvShard, group=None, out: torch.Tensor = None) -> torch.Tensor:
     """All-gathers a per-aviary tensor [E_local, ...] into [E_total, ...] (same order as a single-GPU run).
-    Off the step path: call it only where the learner needs one tensor."""
+    Off the step path: call it only where the learner needs one tensor.  (formation.py uses it with `out=` for the
+    positions of a formation sharded by drones: same partition, the unit is then a drone.)"""
     if shard.world == 1:
-        return local
+        if out is None:
+            return local
+        out.copy_(local)
+        return out
     counts = [shard_envs(shard.total, r, shard.world).count for r in range(shard.world)]
     if len(set(counts)) == 1:
-        out = torch.empty((shard.total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        if out is None:
+            out = torch.empty((shard.total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         return out
     # uneven shards: collectives need equal sizes, so pad every shard to the largest and trim after the gather
+    out_arg = out
     m = max(counts)
     padded = torch.zeros((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     padded[:local.shape[0]] = local
     out = torch.empty((shard.world * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, padded, group=group)
-    return torch.cat([out[r * m:r * m + c] for r, c in enumerate(counts)], dim=0)
+    res = torch.cat([out[r * m:r * m + c] for r, c in enumerate(counts)], dim=0)
+    if out_arg is not None:
+        out_arg.copy_(res)
+        return out_arg
+    return res

@@ -15,6 +15,8 @@
  *   qs_pid_control   <- DSLPIDControl.computeControl (control/DSLPIDControl.py:82-259) and
  *                       BaseControl.computeControlFromState (control/BaseControl.py:55-93)
  *   qs_downwash      <- BaseAviary._downwash (envs/BaseAviary.py:785-811), pairwise term
+ *   qs_downwash_rows / qs_dw_publish <- the same loop for one formation sharded over GPUs (rows = local drones)
+ *   qs_adjacency     <- BaseAviary._getAdjacencyMatrix (envs/BaseAviary.py:658-675)
  *   qs_reset         <- BaseAviary.reset/_housekeeping (envs/BaseAviary.py:220-255,451-505)
  *
  * Conventions
@@ -234,6 +236,43 @@ int qs_pid_control(const QsParams* p, float* pid_state, double control_timestep,
 /* Pairwise downwash within each aviary: fz_out[n] = sum over drones i of the same aviary with dz>0, dxy<10 of
  * -alpha*exp(-.5 (dxy/beta)^2) (force along n's body z).  Reads positions from the state planes. */
 int qs_downwash(const QsParams* p, const QsState* st, int n_envs, int drones_per_env, float* fz_out, void* stream);
+
+/* Downwash with a workspace: like qs_downwash, but first tabulates the bounding boxes of every 32 consecutive drones
+ * (boxes_ws: float [n_envs][ceil(D/32)][8], 16-byte aligned) and then evaluates, per group of 32 rows, only the chunks
+ * whose box can contribute (exact: a skipped pair fails the reference's predicate or its Gaussian is 0.0f). */
+int qs_downwash_boxed(const QsParams* p, const QsState* st, int n_envs, int drones_per_env, float* boxes_ws, float* fz_out, void* stream);
+
+/* Downwash for ONE formation sharded across GPUs (one exchange of positions per substep).
+ * "gathered array": the [n_total][4] positions of the WHOLE formation immediately followed by its chunk boxes
+ * [ceil(n_total/32)][8]; qs_dw_gathered_floats(n_total) floats, 16-byte aligned.  It is filled either by
+ * qs_dw_publish from every rank (positions + boxes pushed into every rank's array, own and NVLink peers), or by an
+ * all-gather of the positions followed by qs_dw_boxes.
+ * qs_downwash_rows: rows_pos = the [n_rows][4] positions this GPU owns (plane 0 of its state).  If ready_flags != NULL
+ * the kernel first waits (bounded, ~2 s, then *err_flag = 1) until ready_flags[r] - seq >= 0 for r < world. */
+#define QS_MAX_PEERS 16
+long long qs_dw_gathered_floats(int n_total);
+int qs_dw_boxes(float* gathered, int n_total, void* stream);
+int qs_downwash_rows(const QsParams* p, const float* rows_pos, int n_rows, const float* gathered, int n_total,
+                     const unsigned* ready_flags, unsigned seq, int world, unsigned* err_flag, float* fz_out, void* stream);
+
+/* Pushes pos[0..n) (+ the boxes of its chunks; offset % 32 == 0) into gathered[r] at drone offset `offset` for every
+ * rank r < world (device pointers in a HOST array), then stores seq to flags[r][rank] with release semantics.
+ * counter: one zeroed device word owned by the caller (inter-CTA arrival count, reset by the kernel). */
+int qs_dw_publish(const float* pos, int n, int offset, float* const* gathered, int n_total, unsigned* const* flags, int world, int rank,
+                  unsigned seq, unsigned* counter, void* stream);
+
+/* CUDA IPC for the exchange buffers of one-process-per-GPU runs: export the 64-byte handle of the allocation that
+ * contains ptr plus ptr's byte offset in it; import maps a peer's handle into this process (peer access enabled
+ * lazily) and returns the peer's ptr.  Import a given handle once per process. */
+int qs_ipc_export(const void* ptr, void* handle64, unsigned long long* offset);
+int qs_ipc_import(const void* handle64, unsigned long long offset, void** ptr_out);
+
+/* cudaDeviceEnablePeerAccess(peer_device) for the current device; already-enabled is not an error. */
+int qs_enable_peer_access(int peer_device);
+
+/* BaseAviary._getAdjacencyMatrix (envs/BaseAviary.py:658-675) for every aviary: out[e][i][j] = 1 if i == j or
+ * |pos_i - pos_j| < radius else 0 (unsigned char [E][D][D]). */
+int qs_adjacency(const QsState* st, int n_envs, int drones_per_env, double radius, unsigned char* out, void* stream);
 
 /* Reset envs to their initial pose.  mask: [E] bytes, nullable = all envs.  Zeroes velocities, body rates,
  * last_rpm, step counter; with reset_pid != 0 also the PID state (the reference never does).

@@ -187,6 +187,17 @@ def downwash_body_z(P, pos, group_size=None):
     return np.sum(np.where(act, f, 0.0), axis=2).astype(pos.dtype)
 
 
+def adjacency_matrix(pos, radius):
+    """BaseAviary._getAdjacencyMatrix (envs/BaseAviary.py:658-675): identity plus 1 where
+    |pos_i - pos_j| < NEIGHBOURHOOD_RADIUS.  `pos` is [E, D, 3]; returns float64 [E, D, D]."""
+    d = pos[:, :, None, :] - pos[:, None, :, :]
+    dist = np.sqrt(np.sum(d * d, axis=-1))
+    adj = (dist < radius).astype(np.float64)
+    idx = np.arange(pos.shape[1])
+    adj[:, idx, idx] = 1.0
+    return adj
+
+
 def dynamics_substep(P, rpm, pos, quat, vel, rpy_rates, effects=0, rpm_prev=None, dw_fz=None, rpy=None):
     """BaseAviary._dynamics (envs/BaseAviary.py:815-877) for a batch [..., ] of drones.
 

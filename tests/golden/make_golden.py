@@ -261,6 +261,20 @@ def main():
         out.update(flat(dm.value, dict(pos=env.pos.copy(), quat=env.quat.copy(), rpy=env.rpy.copy(), vel=env.vel.copy(), rpm=rpm,
                                        gnd_thrust=gnd, drag_body=drag_body, downwash_body_z=dw)))
     save("effects_formula", **out)
+    adjacency_fixture()
+
+
+def adjacency_fixture():
+    """BaseAviary._getAdjacencyMatrix (BaseAviary.py:658-675) on random swarms, three neighbourhood radii."""
+    rng = np.random.default_rng(77)
+    out = {}
+    for k, (nd, radius) in enumerate([(40, 0.8), (33, 2.5), (7, 1e-3)]):
+        xyz = rng.uniform(-1.5, 1.5, (nd, 3)).astype(np.float32).astype(np.float64)
+        xyz[:, 2] += 2.0
+        with quiet():
+            env = R.CtrlAviary(num_drones=nd, neighbourhood_radius=radius, initial_xyzs=xyz, physics=R.Physics.DYN)
+        out.update(flat("case%d" % k, dict(pos=env.pos.copy(), radius=np.float64(radius), adjacency=env._getAdjacencyMatrix())))
+    save("adjacency", **out)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,203 @@
+"""-m gpu: neighbourhood query, culled downwash and the sharded-formation exchange."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from qs_testlib import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _imports():
+    from gym_pybullet_drones_b200 import _native as N
+    from gym_pybullet_drones_b200.envs import CtrlAviary
+    from gym_pybullet_drones_b200.formation import FormationShard, morton_order
+    from gym_pybullet_drones_b200.utils.enums import Physics
+    from oracle import dyn_oracle as O
+    return N, CtrlAviary, FormationShard, morton_order, Physics, O
+
+
+def config4_grid(nx, ny, pitch=0.15):
+    """BASELINE config 4 geometry: grid in xy with 0.15 m pitch, z = 0.1 + 0.05 (i mod 16).  Used for
+    STATIC force evaluations only (nearly equal heights make the dynamics ill-conditioned, see stacks())."""
+    k = np.arange(nx * ny)
+    j, i = np.divmod(k, nx)
+    return np.stack([pitch * i, pitch * j, 0.1 + 0.05 * (k % 16)], axis=1).astype(np.float32).astype(np.float64)
+
+
+def stacks(nx, ny, pitch=1.6):
+    """nx x ny stacks of 4 drones 1.5 m apart with small lateral offsets (well-conditioned dynamics: the model's
+    1/dz^2 term is singular for nearly equal heights, so drones of one layer never get within the Gaussian's reach)."""
+    k = np.arange(nx * ny * 4)
+    st, ly = k // 4, k % 4
+    return np.stack([pitch * (st % nx) + 0.04 * ly, pitch * (st // nx) - 0.03 * ly, 0.5 + 1.5 * ly], axis=1).astype(np.float32).astype(np.float64)
+
+
+def _fz(N, env, cull=True, boxed=False):
+    D = env._D
+    fz = torch.zeros(env._E * D, device="cuda")
+    old = os.environ.get("QS_DW_CULL")
+    os.environ["QS_DW_CULL"] = "1" if cull else "0"
+    sp = torch.cuda.current_stream().cuda_stream
+    try:
+        if boxed:
+            ws = torch.zeros((env._E, (D + 31) // 32, 8), device="cuda")
+            N.check(N.lib().qs_downwash_boxed(C.byref(env._P), C.byref(env._st), env._E, D, ws.data_ptr(), fz.data_ptr(), sp), "qs_downwash_boxed")
+        else:
+            N.check(N.lib().qs_downwash(C.byref(env._P), C.byref(env._st), env._E, D, fz.data_ptr(), sp), "qs_downwash")
+    finally:
+        if old is None:
+            del os.environ["QS_DW_CULL"]
+        else:
+            os.environ["QS_DW_CULL"] = old
+    return fz.cpu().numpy()
+
+
+def test_adjacency_golden(golden):
+    """BaseAviary._getAdjacencyMatrix of the unmodified reference on three random swarms: bit-exact."""
+    N, CtrlAviary, _, _, Physics, _ = _imports()
+    g = golden("adjacency")
+    for k in range(3):
+        pos, radius = g["case%d_pos" % k], float(g["case%d_radius" % k])
+        env = CtrlAviary(num_drones=pos.shape[0], neighbourhood_radius=radius, initial_xyzs=pos, physics=Physics.DYN)
+        adj = env._getAdjacencyMatrix()
+        assert adj.dtype == np.float64 and np.array_equal(adj, g["case%d_adjacency" % k])
+
+
+@pytest.mark.parametrize("E,D,radius", [(3, 1000, 0.7), (1, 4096, 1.1), (5, 37, np.inf), (2, 512, 0.0)])
+def test_adjacency_vs_oracle(E, D, radius):
+    """Vector query [E, D, D] against the NumPy restatement: ragged D (scalar stores), D % 16 == 0 (16-byte stores),
+    several column tiles, radius 0 (identity) and inf (all ones)."""
+    N, CtrlAviary, _, _, Physics, O = _imports()
+    rng = np.random.default_rng(3)
+    pos = rng.uniform(-2, 2, (E, D, 3)).astype(np.float32).astype(np.float64)
+    env = CtrlAviary(num_drones=D, neighbourhood_radius=radius, initial_xyzs=pos, physics=Physics.DYN, num_envs=E)
+    env.reset()
+    adj = env.adjacency().cpu().numpy()
+    ref = O.adjacency_matrix(pos, radius)
+    assert adj.dtype == np.uint8 and np.array_equal(adj, ref.astype(np.uint8))
+    assert np.array_equal(adj, adj.transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("order", ["rows", "morton", "shuffled"])
+def test_downwash_culling_is_exact(order):
+    """Chunk culling only skips pairs that fail the reference's predicate or whose Gaussian is exactly 0.0f: the culled
+    kernel is BIT-identical to the all-pairs evaluation, whatever the index order, and both match the oracle."""
+    N, CtrlAviary, _, morton_order, Physics, O = _imports()
+    xyz = config4_grid(64, 64)
+    if order == "morton":
+        xyz = xyz[morton_order(xyz[:, :2])]
+    elif order == "shuffled":
+        xyz = xyz[np.random.default_rng(1).permutation(len(xyz))]
+    env = CtrlAviary(num_drones=len(xyz), initial_xyzs=xyz, physics=Physics.PYB_DW, num_envs=1)
+    env.reset()
+    ref = O.downwash_body_z(O.OracleParams(), xyz[None])[0]
+    assert np.count_nonzero(ref) > 0.7 * len(xyz)
+    for boxed in (False, True):                      # tiled kernel (qs_downwash) and box-table kernel (qs_downwash_boxed)
+        a, b = _fz(N, env, cull=True, boxed=boxed), _fz(N, env, cull=False, boxed=boxed)
+        assert np.array_equal(a, b), boxed
+        assert relerr(a, ref) < 1e-5, boxed
+
+
+def test_downwash_cutoff_10m_and_ragged_tiles():
+    """Sources beyond the 10 m xy cut-off (BaseAviary.py:800) and a drone count that is no multiple of the tile sizes."""
+    N, CtrlAviary, _, _, Physics, O = _imports()
+    rng = np.random.default_rng(8)
+    D = 777
+    xyz = np.stack([rng.uniform(-9, 9, D), rng.uniform(-9, 9, D), 0.5 + 4.0 * rng.integers(0, 6, D) + rng.uniform(0, 0.3, D)], axis=1)
+    xyz = xyz.astype(np.float32).astype(np.float64)
+    env = CtrlAviary(num_drones=D, initial_xyzs=xyz, physics=Physics.PYB_DW, num_envs=1)
+    env.reset()
+    ref = O.downwash_body_z(O.OracleParams(), xyz[None])[0]
+    for boxed in (False, True):
+        a, b = _fz(N, env, cull=True, boxed=boxed), _fz(N, env, cull=False, boxed=boxed)
+        assert np.array_equal(a, b), boxed
+        assert relerr(a, ref) < 1e-5, boxed
+
+
+def _run_local(FormationShard, Physics, xyz, acts, **kw):
+    env = FormationShard(xyz, physics=Physics.PYB_GND_DRAG_DW, exchange="local", rank=0, world=1, pyb_freq=240, ctrl_freq=48, **kw)
+    env.reset()
+    for a in acts:
+        obs, _, _, _, _ = env.step(torch.from_numpy(a).cuda())
+    torch.cuda.synchronize()
+    return obs.clone(), env._planes.clone()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_formation_shards_p2p_protocol_one_gpu(world):
+    """The push + flag exchange with `world` in-process shards on ONE device, each on its own stream: the states after
+    6 ticks x 5 substeps are bit-identical to the unsharded formation (chunks and row groups are 32 consecutive drones of
+    the GLOBAL index, so the summation order does not depend on the partition), no wait timed out."""
+    N, _, FormationShard, _, Physics, O = _imports()
+    xyz = stacks(16, 12)                                  # 768 drones: 768 / 384 / 256 per rank, all multiples of 32
+    n, T = len(xyz), 6
+    rng = np.random.default_rng(11)
+    hover = O.OracleParams().HOVER_RPM
+    acts = [(hover * (1 + 0.05 * rng.uniform(-1, 1, (1, n, 4)))).astype(np.float32) for _ in range(T)]
+    obs_ref, planes_ref = _run_local(FormationShard, Physics, xyz, acts)
+    shards = [FormationShard(xyz, physics=Physics.PYB_GND_DRAG_DW, exchange="p2p", rank=r, world=world,
+                             pyb_freq=240, ctrl_freq=48) for r in range(world)]
+    if world > 1:
+        for s in shards:
+            s.connect(shards)
+    streams = [torch.cuda.Stream() for _ in shards]
+    torch.cuda.synchronize()
+    for s in shards:
+        s.reset()
+    torch.cuda.synchronize()
+    outs = [None] * world
+    for a in acts:
+        a_dev = torch.from_numpy(a).cuda()
+        torch.cuda.synchronize()
+        for r, s in enumerate(shards):
+            with torch.cuda.stream(streams[r]):
+                outs[r] = s.step(a_dev[:, s.shard.start:s.shard.stop].contiguous())[0]
+    torch.cuda.synchronize()
+    assert not any(s.exchange_timed_out() for s in shards)
+    obs = torch.cat(outs, dim=1)
+    planes = torch.cat([s._planes for s in shards], dim=1)
+    assert torch.equal(obs, obs_ref) and torch.equal(planes, planes_ref)
+
+
+def test_formation_local_vs_oracle():
+    """FormationShard(exchange='local') = CtrlAviary with the external downwash stage, against the O(N^2) oracle."""
+    N, _, FormationShard, _, Physics, O = _imports()
+    xyz = stacks(16, 8)
+    n, T = len(xyz), 8
+    env = FormationShard(xyz, physics=Physics.PYB_GND_DRAG_DW, exchange="local", rank=0, world=1, pyb_freq=240, ctrl_freq=48)
+    ora = O.OracleAviary("ctrl", 1, n, ctrl_freq=48, initial_xyzs=xyz, effects=7)
+    env.reset(); ora.reset()
+    rng = np.random.default_rng(2)
+    for t in range(T):
+        a = (ora.P.HOVER_RPM * (1 + 0.05 * rng.uniform(-1, 1, (1, n, 4)))).astype(np.float32)
+        obs, _, _, _, _ = env.step(torch.from_numpy(a).cuda())
+        o_obs, _, _, _ = ora.step(a)
+        o = obs.cpu().numpy()
+        assert relerr(o[..., 0:3], o_obs[..., 0:3]) < 2e-5, t
+        assert relerr(o[..., 7:16], o_obs[..., 7:16]) < 1e-4, t
+
+
+def test_multi_aviary_boxed_downwash_and_ragged_sizes():
+    """qs_downwash_boxed over several aviaries with a drone count that is no multiple of 32 (partial last chunk and row
+    group), against the oracle and bit-identical to its all-chunks evaluation."""
+    N, CtrlAviary, _, _, Physics, O = _imports()
+    rng = np.random.default_rng(4)
+    E, D = 3, 333
+    xyz = np.stack([rng.uniform(-6, 6, (E, D)), rng.uniform(-6, 6, (E, D)), 0.5 + 3.0 * rng.integers(0, 5, (E, D)) + rng.uniform(0, 0.2, (E, D))], axis=2)
+    xyz = xyz.astype(np.float32).astype(np.float64)
+    env = CtrlAviary(num_drones=D, initial_xyzs=xyz, physics=Physics.PYB_DW, num_envs=E)
+    env.reset()
+    a, b = _fz(N, env, cull=True, boxed=True), _fz(N, env, cull=False, boxed=True)
+    assert np.array_equal(a, b)
+    ref = O.downwash_body_z(O.OracleParams(), xyz).reshape(-1)
+    assert np.count_nonzero(ref) > 0.5 * E * D and relerr(a, ref) < 1e-5
+
+
+def test_p2p_needs_chunk_aligned_shards():
+    _, _, FormationShard, _, Physics, _ = _imports()
+    with pytest.raises(ValueError):
+        FormationShard(stacks(5, 5), physics=Physics.PYB_DW, exchange="p2p", rank=0, world=2)

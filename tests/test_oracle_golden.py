@@ -205,6 +205,13 @@ def test_effect_formulas(golden, model):
     assert np.count_nonzero(g[k + "downwash_body_z"]) > 10
 
 
+def test_adjacency_matrix(golden):
+    g = golden("adjacency")
+    for k in range(3):
+        adj = O.adjacency_matrix(g["case%d_pos" % k][None], float(g["case%d_radius" % k]))[0]
+        assert np.array_equal(adj, g["case%d_adjacency" % k])
+
+
 def test_quaternion_helpers_against_scipy():
     """Bullet's helpers are restated from its published algorithm (library absent): cross-check with scipy."""
     from scipy.spatial.transform import Rotation

@@ -66,3 +66,50 @@ def test_world2_gloo_sharded_equals_single(total):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) == (True, True, True)
+
+
+def _formation_worker(rank, world, port, q):
+    """A formation sharded by DRONES: downwash needs every position each substep (formation.py); the host-side
+    exchange (partition offsets, uneven all-gather into a preallocated buffer) against the unsharded oracle."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import dyn_oracle as O
+        P = O.OracleParams()
+        k = np.arange(27)
+        xyz = np.stack([1.6 * (k // 3) + 0.04 * (k % 3), -0.03 * (k % 3), 0.5 + 1.5 * (k % 3)], axis=1)
+        n = len(xyz)
+        sh = shard_envs(n)
+        rpm = np.full((n, 4), P.HOVER_RPM * 1.02)
+
+        def run(pos, rows, gather):
+            quat = np.tile([0., 0., 0., 1.], (len(rows), 1)); vel = np.zeros((len(rows), 3)); rr = np.zeros((len(rows), 3))
+            pos = pos[rows].copy()
+            buf = torch.zeros((n, 3), dtype=torch.float64)
+            for _ in range(12):
+                every = gather(pos, buf)
+                fz = O.downwash_body_z(P, every[None])[0][rows]
+                pos, quat, vel, rr, _ = O.dynamics_substep(P, rpm[rows], pos, quat, vel, rr, effects=O.EFFECT_DW, dw_fz=fz)
+            return pos
+
+        mine = np.arange(sh.start, sh.stop)
+        local = run(xyz, mine, lambda p, buf: all_gather_envs(torch.from_numpy(p), sh, out=buf).numpy())
+        g = all_gather_envs(torch.from_numpy(local), sh)
+        if rank == 0:
+            ref = run(xyz, np.arange(n), lambda p, buf: p)
+            q.put((bool(np.array_equal(g.numpy(), ref)), bool(np.abs(ref - xyz).max() > 1e-6)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_formation_sharded_by_drones():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_formation_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == (True, True)

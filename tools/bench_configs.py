@@ -115,10 +115,52 @@ rpm = torch.full((1, Dn, 4), float(env.HOVER_RPM), device=dev)
 ms = timed(lambda: env.step(rpm), 50, 5)
 import ctypes as C
 from gym_pybullet_drones_b200 import _native as N
-fz = torch.zeros(Dn, device=dev)
-msdw = timed(lambda: N.lib().qs_downwash(C.byref(env._P), C.byref(env._st), 1, Dn, fz.data_ptr(), torch.cuda.current_stream().cuda_stream), 50, 5)
+import os
+from gym_pybullet_drones_b200.formation import morton_order
+
+
+def dw_ms(e, cull, boxed=True):
+    os.environ["QS_DW_CULL"] = "1" if cull else "0"
+    f = torch.zeros(e._D, device=dev)
+    ws = torch.zeros(((e._D + 31) // 32, 8), device=dev)
+    sp = torch.cuda.current_stream().cuda_stream
+    if boxed:
+        t = timed(lambda: N.lib().qs_downwash_boxed(C.byref(e._P), C.byref(e._st), 1, e._D, ws.data_ptr(), f.data_ptr(), sp), 50, 5)
+    else:
+        t = timed(lambda: N.lib().qs_downwash(C.byref(e._P), C.byref(e._st), 1, e._D, f.data_ptr(), sp), 50, 5)
+    os.environ["QS_DW_CULL"] = "1"
+    return t
+
+
+env.reset()                                   # the force kernel is timed on the formation's reset geometry
+ms_all, ms_cull = dw_ms(env, False), dw_ms(env, True)
+ms_all_tiled, ms_cull_tiled = dw_ms(env, False, boxed=False), dw_ms(env, True, boxed=False)
+env_m = CtrlAviary(num_drones=Dn, initial_xyzs=xyz[morton_order(xyz[:, :2])], physics=Physics.PYB_GND_DRAG_DW, pyb_freq=240, ctrl_freq=240, num_envs=1)
+env_m.reset()
+ms_morton, ms_morton_tiled = dw_ms(env_m, True), dw_ms(env_m, True, boxed=False)
+ms_step_morton = timed(lambda: (env_m.reset(), env_m.step(rpm)), 20, 3)
 out["config4_formation_16384_gnd_drag_dw"] = {"drones": Dn, "S": 1, "ms_per_step": ms, "drone_steps_per_s": Dn / (ms * 1e-3),
-                                              "downwash_kernel_ms": msdw, "pairs_per_s": Dn * Dn / (msdw * 1e-3),
-                                              "note": "pairwise term is FP32 ALU/SFU bound (N^2 = 2.7e8 pairs per substep), not HBM bound"}
+                                              "downwash_kernel_ms": ms_cull, "pairs_per_s": Dn * Dn / (ms_cull * 1e-3),
+                                              "downwash_ms": {"all_pairs": ms_all, "culled_row_major": ms_cull, "culled_morton_order": ms_morton,
+                                                              "tiled_kernel_all_pairs": ms_all_tiled, "tiled_kernel_culled_row_major": ms_cull_tiled,
+                                                              "tiled_kernel_culled_morton_order": ms_morton_tiled},
+                                              "reset_plus_step_ms_morton_order": ms_step_morton,
+                                              "pairs_per_s_all_pairs": Dn * Dn / (ms_all * 1e-3),
+                                              "note": "pairwise term is FP32 ALU/SFU bound, not HBM bound; qs_downwash_boxed: boxes kernel + box-table kernel; exact culling skips chunks that cannot contribute (pairs/s counts all N^2 pairs); ms_per_step = steps from a drifting formation"}
+adj = torch.empty((1, Dn, Dn), dtype=torch.uint8, device=dev)
+env.NEIGHBOURHOOD_RADIUS = 1.0
+ms_adj = timed(lambda: env.adjacency(adj), 50, 5)
+out["adjacency_16384"] = {"drones": Dn, "S": 1, "ms_per_step": ms_adj, "drone_steps_per_s": Dn / (ms_adj * 1e-3), "alg_bytes": Dn,
+                          "hbm_frac": Dn * Dn / (ms_adj * 1e-3) / 1e9 / PEAK, "note": "qs_adjacency: N^2 bytes written per query (268 MB)"}
+del env_m, adj
+# a formation 4x larger: 65536 drones, 256x256 grid, Morton order
+Db = 65536
+ib = np.arange(Db)
+xb = np.stack([0.15 * (ib % 256), 0.15 * (ib // 256), 0.1 + 0.05 * (ib % 16)], axis=1)
+env_b = CtrlAviary(num_drones=Db, initial_xyzs=xb[morton_order(xb[:, :2])], physics=Physics.PYB_GND_DRAG_DW, pyb_freq=240, ctrl_freq=240, num_envs=1)
+env_b.reset()
+ms_b = dw_ms(env_b, True)
+out["formation_65536_downwash_culled_morton"] = {"drones": Db, "S": 1, "ms_per_step": ms_b, "drone_steps_per_s": Db / (ms_b * 1e-3),
+                                                  "pairs_per_s": Db * Db / (ms_b * 1e-3), "note": "downwash kernel only; 4.3e9 pairs, culled"}
 json.dump(out, open("gpurun_out/configs_r01.json", "w"), indent=1)
 print(json.dumps(out, indent=1))
