@@ -1123,7 +1123,7 @@ __global__ void __launch_bounds__(128) dw_publish_kernel(const __grid_constant__
 // |pos_i - pos_j| < radius.  HBM-write bound (D^2 bytes per aviary): a thread produces 16 columns of one row as one
 // 16-byte store, a warp 512 contiguous bytes; the 512 column positions of a CTA sit in shared memory.  The
 // comparison is made in float32 and re-evaluated in float64 (sqrt(dx^2+dy^2+dz^2) < radius, the reference's
-// arithmetic) only when the float32 value is within 1e-4 relative of the threshold.
+// arithmetic) only when the float32 value is within 2e-4 relative of the threshold (warp-uniform rare branch).
 // ---------------------------------------------------------------------------------------------------------
 struct AdjArgs {
     const float* planes;
@@ -1147,6 +1147,8 @@ __global__ void __launch_bounds__(256) adjacency_kernel(const __grid_constant__ 
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float r2f = (float)(a.radius * a.radius);
+    float r2lo = r2f * (1.f - 2e-4f), r2hi = r2f * (1.f + 2e-4f);           // outside [lo, hi] float32 decides
+    if (a.radius < 0.0) r2lo = r2hi = -1.f;                                 // |d| < negative radius: never
     const bool vec = (a.D % 16) == 0;
     for (int rr = warp; rr < kAdjRows; rr += 8) {
         const int i = r0 + rr;
@@ -1157,19 +1159,22 @@ __global__ void __launch_bounds__(256) adjacency_kernel(const __grid_constant__ 
         unsigned word = 0u;
 #pragma unroll
         for (int q = 0; q < kAdjCols / 32; ++q) {
-            const int cidx = q * 32 + lane;
-            const float4 o = cols[cidx];
+            const float4 o = cols[q * 32 + lane];
             const float dx = o.x - me.x, dy = o.y - me.y, dz = o.z - me.z;
             const float d2 = dx * dx + dy * dy + dz * dz;
-            bool near = d2 < r2f;
-            if (fabsf(d2 - r2f) <= 1e-4f * r2f) {
-                const double ex = (double)me.x - (double)o.x, ey = (double)me.y - (double)o.y, ez = (double)me.z - (double)o.z;
-                near = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez))) < a.radius;
+            bool near = d2 < r2lo;
+            const bool amb = !near && !(d2 > r2hi);
+            if (__any_sync(0xffffffffu, amb)) {                          // rare: within 2e-4 of the threshold -> reference arithmetic
+                if (amb) {
+                    const double ex = (double)me.x - (double)o.x, ey = (double)me.y - (double)o.y, ez = (double)me.z - (double)o.z;
+                    near = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez))) < a.radius;
+                }
             }
-            near = (near || c0 + cidx == i) && (c0 + cidx < a.D);
             const unsigned bits = __ballot_sync(0xffffffffu, near);
             if (lane == q) word = bits;
         }
+        const int ci = i - c0;                                            // identity (BaseAviary.py:666)
+        if (ci >= 0 && ci < kAdjCols && lane == (ci >> 5)) word |= 1u << (ci & 31);
         const unsigned h = (__shfl_sync(0xffffffffu, word, lane >> 1) >> ((lane & 1) * 16)) & 0xffffu;
         unsigned w[4];
 #pragma unroll

@@ -67,10 +67,10 @@ def test_adjacency_golden(golden):
         assert adj.dtype == np.float64 and np.array_equal(adj, g["case%d_adjacency" % k])
 
 
-@pytest.mark.parametrize("E,D,radius", [(3, 1000, 0.7), (1, 4096, 1.1), (5, 37, np.inf), (2, 512, 0.0)])
+@pytest.mark.parametrize("E,D,radius", [(3, 1000, 0.7), (1, 4096, 1.1), (5, 37, np.inf), (2, 512, 0.0), (2, 48, -1.0)])
 def test_adjacency_vs_oracle(E, D, radius):
     """Vector query [E, D, D] against the NumPy restatement: ragged D (scalar stores), D % 16 == 0 (16-byte stores),
-    several column tiles, radius 0 (identity) and inf (all ones)."""
+    several column tiles, radius 0 and negative (identity) and inf (all ones)."""
     N, CtrlAviary, _, _, Physics, O = _imports()
     rng = np.random.default_rng(3)
     pos = rng.uniform(-2, 2, (E, D, 3)).astype(np.float32).astype(np.float64)
