@@ -81,6 +81,44 @@ copy); trimming the step kernel's fixed shared memory so 18 instead of 15 CTAs f
 drones, 138.6 -> 136.0 us at 1 M: not adopted).  Box-to-box spread of the same binary is up to ~10 % at 1 M drones (158-176 us), so only same-box A/B numbers are
 compared.
 """)
+fpath = os.path.join(ROOT, "profiles", "r01_formation.json")
+if os.path.isfile(fpath):
+    F = json.load(open(fpath))
+    L.append("""
+## Formations: downwash with exact chunk culling, neighbourhood query, one formation over several GPUs (`r01_formation.json`)
+
+Downwash force kernel on the config-4 geometry (128 x 128 grid, 0.15 m pitch, z = 0.1 + 0.05 (i mod 16)), reset positions
+(`r01_configs.json: config4_formation_16384_gnd_drag_dw.downwash_ms`); every variant returns the SAME bits as its own
+all-pairs evaluation (`tests/test_gpu_formation.py::test_downwash_culling_is_exact`):
+
+| kernel | all pairs | culled, row-major order | culled, Morton order |
+|---|---|---|---|""")
+    dm = cfg.get("config4_formation_16384_gnd_drag_dw", {}).get("downwash_ms", {})
+    if dm:
+        L.append("| `qs_downwash` (1024-source tiles in shared memory) | %.0f us | %.0f us | %.0f us |" % (dm["tiled_kernel_all_pairs"] * 1e3, dm["tiled_kernel_culled_row_major"] * 1e3, dm["tiled_kernel_culled_morton_order"] * 1e3))
+        L.append("| `qs_downwash_boxed` (box table, 32-row CTAs; incl. the 4 us boxes kernel) | %.0f us | %.0f us | %.0f us |" % (dm["all_pairs"] * 1e3, dm["culled_row_major"] * 1e3, dm["culled_morton_order"] * 1e3))
+    L.append("""
+First version of the kernel (IEEE division + expf, 256-source tiles, no culling): 502 us = 5.3e11 pairs/s.  SFU
+reciprocal/exp2 + per-pair underflow early-out: 207 us all pairs (1.3e12 pairs/s); with chunk culling 31-33 us.
+65 536-drone formation (256 x 256 grid, Morton order): %s us per evaluation.
+
+One formation sharded over GPUs (`tools/formation_multi_gpu.py`, one process per GPU; per physics substep: exchange of
+positions + boxes, then the force of the local rows; CUDA events, max over ranks; `stage` = exchange + force,
+measured on the reset geometry):
+
+| drones | GPUs | bit-identical to the unsharded run (10 ticks x 5 substeps, gnd + drag + downwash) | stage, NCCL all-gather + boxes kernel | stage, push + flags over NVLink peer memory | parts: NCCL all-gather / publish kernel / force kernel |
+|---|---|---|---|---|---|""" % ("%.0f" % (cfg.get("formation_65536_downwash_culled_morton", {}).get("ms_per_step", float("nan")) * 1e3)))
+    for key in sorted(k for k in F if k.startswith("world")):
+        d = F[key]
+        bit = "yes (NCCL and p2p)" if d.get("nccl_bit_identical_to_unsharded") and d.get("p2p_bit_identical_to_unsharded") else ("not checked (timing only)" if "p2p_bit_identical_to_unsharded" not in d else "NO")
+        L.append("| %d | %d | %s | %.1f us | %.1f us%s | %.1f / %.1f / %.1f us |" % (
+            d["drones"], d["world"], bit, d["stage_us_nccl"], d["stage_us_p2p"],
+            (" (unsharded single launch path: %.1f us)" % d["stage_us_local"]) if "stage_us_local" in d else "",
+            d["part_us_nccl_all_gather"], d["part_us_publish_kernel"], d["part_us_downwash_rows_kernel"]))
+    a = F.get("adjacency_final")
+    if a:
+        L.append("\n`qs_adjacency` (BaseAviary._getAdjacencyMatrix), 16 384 drones, radius 1 m: %.0f us for the 268 MB matrix = %.0f GB/s written (%.2f of the %.0f GB/s copy peak; instruction-bound: ~13 instructions per 32 pairs)." % (a["adjacency_16384_ms"] * 1e3, a["GBps_written"], a["GBps_written"] / r["peak"], r["peak"]))
+
 L.append("\n## ncu captures (`ncu --set full --clock-control none --import-source on`, one GPU, `bench.py --steps 20`)\n")
 for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_*_ncu.md"))):
     L.append("* `%s` — %s" % (os.path.basename(f), open(f).read().split("\n")[2]))
