@@ -122,6 +122,7 @@ measured on the reset geometry):
 L.append("\n## ncu captures (`ncu --set full --clock-control none --import-source on`, one GPU, `bench.py --steps 20`)\n")
 for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_*_ncu.md"))):
     L.append("* `%s` — %s" % (os.path.basename(f), open(f).read().split("\n")[2]))
+L.append("* `r01_step_kernel_stall_breakdown.md` — where a warp's time goes in the step kernel at the bench size (stall reasons, opcode classes, program regions) and why the launch is latency-bound there.")
 L.append("* `r01_a_launches.csv` — launch list of the first correct kernel (setup part only).")
 try:
     import collections, csv
