@@ -19,6 +19,10 @@ sufficient: a rank can publish sequence k+2 only after its own downwash k+1 has 
 raises k+1 only after its downwash k -- the last reader of buffer k & 1 -- has finished.  `exchange="nccl"` replaces
 1. by `all_gather_into_tensor` (the baseline the p2p path is measured against, and the path the gloo CPU tests
 cover); `exchange="local"` is the single-GPU case.
+
+Lifetime and limits: the shards of one formation are created and destroyed collectively (a peer's mapping of this
+rank's exchange allocation stays open for the life of the process); `exchange="p2p"` needs a drone count that is a
+multiple of 32 x world; the p2p stage is not CUDA-graph capturable (the sequence number is a launch parameter).
 """
 import ctypes as C
 
