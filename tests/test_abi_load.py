@@ -55,6 +55,41 @@ def test_argument_errors_without_a_gpu():
         pass
 
 
+def test_header_is_plain_c99():
+    """include/quadsim.h is the drop-in boundary: it must compile as C (what cgo / JNI / ctypes-style bindings see), not
+    only as C++."""
+    import subprocess
+    h = os.path.join(ROOT, "include", "quadsim.h")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", h],
+                ["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", h]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_formation_entry_points_validate_arguments():
+    lib = N.lib()
+    P = N.QsParams()
+    buf = (C.c_float * 256)()
+    a = C.addressof(buf)
+    a16 = (a + 15) & ~15
+    assert lib.qs_dw_gathered_floats(0) == 0 and lib.qs_dw_gathered_floats(33) == 4 * 33 + 8 * 2
+    assert lib.qs_dw_boxes(None, 8, None) == -1 and lib.qs_dw_boxes(a16 + 4, 8, None) == -2 and lib.qs_dw_boxes(a16, 0, None) == -3
+    assert lib.qs_downwash_rows(C.byref(P), a16, 8, None, 8, None, 0, 0, None, a16, None) == -1
+    assert lib.qs_downwash_rows(C.byref(P), a16, 8, a16, 8, a16, 1, 17, None, a16, None) == -3          # world > QS_MAX_PEERS
+    g = (C.c_void_p * 2)(a16, a16)
+    f = (C.c_void_p * 2)(a16, a16)
+    assert lib.qs_dw_publish(a16, 64, 16, g, 128, f, 2, 0, 1, a16, None) == -2                          # offset not a multiple of 32
+    assert b"multiple of 32" in lib.qs_last_error()
+    assert lib.qs_dw_publish(a16, 40, 0, g, 128, f, 2, 0, 1, a16, None) == -2                           # a chunk would straddle ranks
+    assert lib.qs_dw_publish(a16, 64, 96, g, 128, f, 2, 0, 1, a16, None) == -3                          # slice beyond n_total
+    assert lib.qs_dw_publish(a16, 64, 0, g, 128, f, 2, 2, 1, a16, None) == -3                           # rank outside world
+    st = N.QsState()
+    assert lib.qs_adjacency(C.byref(st), 1, 4, 1.0, None, None) == -1
+    assert lib.qs_downwash_boxed(C.byref(P), C.byref(st), 1, 4, None, None, None) == -1
+    off = C.c_ulonglong(0)
+    assert lib.qs_ipc_export(None, buf, C.byref(off)) == -1 and lib.qs_ipc_import(None, 0, None) == -1
+
+
 def test_product_package_does_not_import_the_oracle():
     """The oracle is test infrastructure: nothing under the product package may reference it."""
     pkg = os.path.join(ROOT, "gym_pybullet_drones_b200")
