@@ -1478,21 +1478,37 @@ int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const
     QsStepIO dio = *io;
     dio.action = h->action_dev;
     if (int rc = qs_step(p, st, &dio, act_type, task, n_envs, drones_per_env, substeps, effects, flags, stream)) return rc;
+    volatile int* marker = want_final ? h->n_final_host : nullptr;
+    if (marker) *marker = -1;
     cudaMemcpyAsync(h->reward_host, io->reward, (size_t)n_envs * 4, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(h->terminated_host, io->terminated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(h->truncated_host, io->truncated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
     if (io->done && h->done_host) cudaMemcpyAsync(h->done_host, io->done, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
     if (want_final) {
-        // the flags are 100 KB: wait for them, pick the finished aviaries, and queue their rows behind the observation copy
+        // The flags are 100 KB, the observations 19 MB.  A 4-byte copy queued behind the flag copies is their completion
+        // marker (n_final_host, preset to -1: no reward has that bit pattern); the observation copy is queued right
+        // after it, so it is in flight while the host waits for the marker, picks the finished aviaries and queues
+        // their rows behind it.
+        cudaMemcpyAsync(const_cast<int*>(marker), io->reward, 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(h->obs_host, io->obs, (size_t)N * od * 4, cudaMemcpyDeviceToHost, s);
         if (trace) t1 = now();
-        e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) return cuda_fail(e, "qs_step_host sync(flags)");
+        {
+            const double t_spin = now();
+            unsigned it = 0;
+            while (*marker == -1) {
+                if ((++it & 1023u) == 0 && now() - t_spin > 50000.0) {               // 50 ms: fall back to a full wait
+                    e = cudaStreamSynchronize(s);
+                    if (e != cudaSuccess) return cuda_fail(e, "qs_step_host sync(flags)");
+                    break;
+                }
+            }
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);                  // the flag arrays are read after the marker
         if (trace) t2 = now();
         int k = 0;
         for (int ev = 0; ev < n_envs; ++ev)
             if (h->done_host[ev]) h->final_env_host[k++] = ev;
         *h->n_final_host = k;
-        cudaMemcpyAsync(h->obs_host, io->obs, (size_t)N * od * 4, cudaMemcpyDeviceToHost, s);
         if (k > 0) {
             const int row_floats = drones_per_env * od;
             cudaMemcpyAsync(h->final_env_dev, h->final_env_host, (size_t)k * 8, cudaMemcpyHostToDevice, s);

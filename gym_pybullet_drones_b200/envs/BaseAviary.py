@@ -280,7 +280,8 @@ class BaseAviary(Env):
         self._h_trunc = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
         self._hcur = 0
         self._h_done = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
-        self._h_nfinal = np.zeros(1, np.int32)
+        self._h_nfinal_t = torch.zeros((1,), dtype=torch.int32).pin_memory()      # also the flag-copy completion marker of qs_step_host
+        self._h_nfinal = self._h_nfinal_t.numpy()
         self._h_idx = torch.zeros((E,), dtype=torch.int64).pin_memory()
         self._idx_dev = torch.zeros((E,), dtype=torch.int64, device=dev)
         if self._final_obs is not None:

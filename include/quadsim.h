@@ -180,7 +180,7 @@ typedef struct QsHostIO {
     unsigned char* done_host;        /* out [E] */
     float* final_obs_host;           /* out: rows [k][D][obs_dim] of the k aviaries that finished (SAME_STEP autoreset); nullable */
     long long* final_env_host;       /* out [E]: their aviary indices, ascending (pinned; doubles as the upload staging) */
-    int* n_final_host;               /* out: k */
+    int* n_final_host;               /* out: k (pinned: it doubles as the completion marker of the flag copies) */
     float* action_dev;               /* caller-owned device scratch [N][A] */
     long long* final_env_dev;        /* caller-owned device scratch [E] */
     float* final_rows_dev;           /* caller-owned device scratch [E][D][obs_dim] */

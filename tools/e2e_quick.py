@@ -1,4 +1,12 @@
-import time, numpy as np, torch, json, sys
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_pybullet_drones_b200.envs import MultiHoverAviary
 from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
 E=32768
