@@ -341,6 +341,39 @@ def main():
             except Exception as ex:  # pragma: no cover
                 sweep[str(n)] = {"error": repr(ex)}
         extras["drones_per_launch_sweep"] = sweep
+    # two of the rotating batches in flight at once (even batches on one stream, odd ones on another): how much of the
+    # one-wave launch latency independent batches can hide.  Reported only; the headline keeps one batch at a time.
+    try:
+        if R % 2 == 0:
+            s_even, s_odd = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            cur = torch.cuda.current_stream(dev)
+
+            def run2(n):
+                for k in range(n):
+                    i = k % R
+                    with torch.cuda.stream(s_even if (i & 1) == 0 else s_odd):
+                        envs[i].step(acts[i])
+
+            torch.cuda.synchronize()
+            run2(64)
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nrep = max(64, min(a.steps, 1000))
+            q0.record(cur)
+            s_even.wait_stream(cur)
+            s_odd.wait_stream(cur)
+            run2(nrep)
+            cur.wait_stream(s_even)
+            cur.wait_stream(s_odd)
+            q1.record(cur)
+            torch.cuda.synchronize()
+            ms2 = q0.elapsed_time(q1) / nrep
+            extras["two_batches_in_flight"] = {"ms_per_step": ms2, "value": DRONES_PER_GPU * world / (ms2 * 1e-3), "unit": METRIC,
+                                               "hbm_frac": ALG_BYTES * DRONES_PER_GPU / (ms2 * 1e-3) / 1e9 / peak_gbs,
+                                               "note": "same launches, even/odd batches on two streams (rank-local, not max over ranks)"}
+    except Exception as ex:  # pragma: no cover
+        extras["two_batches_in_flight"] = {"error": repr(ex)}
+        torch.cuda.synchronize()
     # fused multi-tick rollout (qs_rollout): T ticks per launch, device-generated uniform actions, obs written as [T,N,72]
     try:
         T = 32
