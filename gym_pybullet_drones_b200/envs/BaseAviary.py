@@ -96,6 +96,13 @@ class BaseAviary(Env):
         self._lib = N.lib()
         if gui or record:
             warnings.warn("gui/record are not available on the GPU simulator (no renderer); ignored")
+        if physics != Physics.DYN:
+            # the reference's PYB* members run Bullet's solver (ground plane, collisions); here every member runs the
+            # explicit DYN integrator (BaseAviary.py:815-892), PYB_* adding the matching aerodynamic terms
+            warnings.warn("Physics.%s runs the explicit Physics.DYN model on the GPU simulator%s: there is no Bullet solver, "
+                          "no ground plane and no collisions (a drone below z=0 keeps falling); pass physics=Physics.DYN "
+                          "to silence this warning" % (physics.name, "" if physics == Physics.PYB else " plus the %s force terms" % physics.value),
+                          stacklevel=3)
         if vision_attributes:
             raise NotImplementedError("RGB observations need PyBullet's renderer; only ObservationType.KIN is supported")
         #### Constants (BaseAviary.py:74-128) ######################
@@ -464,6 +471,8 @@ class BaseAviary(Env):
         if type(action) is torch.Tensor and self.VECTORIZED and self._simple_launch:
             #### fast path: device tensor in, device tensors out, one kernel launch, no other device work ####
             a = action
+            if a.numel() != self._N * self._A:
+                raise ValueError("action must have %d x %d x %d elements, got shape %s" % (self._E, self._D, self._A, tuple(a.shape)))
             if a.dtype is not torch.float32 or a.device != self.device or not a.is_contiguous() or (a.data_ptr() & 15):
                 self._action_dev.copy_(a.reshape(self._N, self._A))
                 a = self._action_dev

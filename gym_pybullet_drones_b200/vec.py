@@ -56,7 +56,10 @@ class SB3VecAviary(_Base):
         self._ep_len += 1
         infos = [{} for _ in range(self.num_envs)]
         if dones.any():
-            idx = info["final_obs_env"]
+            idx = info.get("final_obs_env")
+            if idx is None:
+                raise RuntimeError("SB3VecAviary needs an env stepped through qs_step_host (autoreset='same_step', "
+                                   "drones_per_env <= 128): this env did not report the finished aviaries")
             now = round(time.time() - self._t0, 6)
             for k, i in enumerate(idx):
                 infos[i] = {"terminal_observation": info["final_obs"][k],
