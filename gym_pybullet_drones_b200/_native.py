@@ -11,10 +11,11 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("QS_LIBQUADSIM", os.path.join(_HERE, "libquadsim.so"))    # override: A/B builds in tools/
-SOURCES = [os.path.join(_HERE, "csrc", "quadsim.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "quad_core.cuh"), os.path.join(_ROOT, "include", "quadsim.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+_CSRC = os.path.join(_HERE, "csrc")
+SOURCES = [os.path.join(_CSRC, f) for f in ("quadsim.cu", "step_fast.cu", "step_general.cu", "rollout.cu", "formation.cu")]
+HEADERS = [os.path.join(_CSRC, "quad_core.cuh"), os.path.join(_CSRC, "qs_common.cuh"), os.path.join(_ROOT, "include", "quadsim.h")]
+OBJ_DIR = os.path.join(_ROOT, "build", "obj")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 # enums of include/quadsim.h
 MODEL_CF2X, MODEL_CF2P, MODEL_RACE = 0, 1, 2
@@ -25,7 +26,7 @@ FLAG_AUTORESET_SAME_STEP, FLAG_AUTORESET_NEXT_STEP, FLAG_RPY_F32 = 1, 2, 4
 FLAG_AUTORESET_CLEARS_PID, FLAG_AUTORESET_CLEARS_HISTORY = 8, 16
 FLAG_OBS_STATE20 = 32
 FLAG_SKIP_EPILOGUE, FLAG_RPM_FROM_LAST = 0x100, 0x200
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _d = C.c_double
 
@@ -52,7 +53,7 @@ class QsState(C.Structure):
     _fields_ = [
         ("planes", C.c_void_p), ("last_rpm", C.c_void_p), ("step_counter", C.c_void_p), ("pending_reset", C.c_void_p),
         ("pid", C.c_void_p), ("init_pos", C.c_void_p), ("init_quat", C.c_void_p), ("target_pos", C.c_void_p),
-        ("tables_per_env", C.c_int), ("pad_", C.c_int),
+        ("pos_f32", C.c_void_p), ("tables_per_env", C.c_int), ("pad_", C.c_int),
     ]
 
 
@@ -90,19 +91,36 @@ MAX_PEERS = 16
 
 
 def build(force=False, verbose=False):
-    """Compile libquadsim.so in-tree for sm_100a with nvcc (no torch headers; a few seconds)."""
-    newest_src = max(os.path.getmtime(p) for p in SOURCES + HEADERS)
-    if not force and os.path.isfile(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest_src:
-        return LIB_PATH
+    """Compile libquadsim.so in-tree for sm_100a with nvcc (no torch headers): one object per translation unit, compiled
+    in parallel and only when its source or a header changed, then linked into the shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+    newest_hdr = max(os.path.getmtime(p) for p in HEADERS)
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.isfile(nvcc):
+        if not force and os.path.isfile(LIB_PATH):
+            return LIB_PATH
         raise RuntimeError("nvcc not found: cannot build libquadsim.so")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs, jobs = [], []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
+        objs.append(obj)
+        if force or not os.path.isfile(obj) or os.path.getmtime(obj) < max(newest_hdr, os.path.getmtime(src)):
+            jobs.append([nvcc] + NVCC_FLAGS + ["-c", "-o", obj, src])
+    if not jobs and os.path.isfile(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(o) for o in objs):
+        return LIB_PATH
+
+    def run(cmd):
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+        return res.stderr
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        logs = list(ex.map(run, jobs))
+    logs.append(run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs))
     if verbose:
-        print(res.stderr)
+        print("\n".join(l for l in logs if l))
     return LIB_PATH
 
 

@@ -12,7 +12,7 @@ from .BaseControl import BaseControl
 
 class DSLPIDControl(BaseControl):
     """PID control class for Crazyflies (DSLPIDControl.py:9), batched: one instance holds the integral and
-    last-rpy state of `num_drones` controllers in a float32 CUDA tensor [9, n] and `computeControl` is one
+    last-rpy state of `num_drones` controllers in a float64 CUDA tensor [9, n] and `computeControl` is one
     launch of qs_pid_control.
 
     With `num_drones=1` and NumPy inputs it behaves like one reference controller:
@@ -32,7 +32,7 @@ class DSLPIDControl(BaseControl):
         self.P_COEFF_FOR, self.I_COEFF_FOR, self.D_COEFF_FOR = co.P_COEFF_FOR, co.I_COEFF_FOR, co.D_COEFF_FOR
         self.P_COEFF_TOR, self.I_COEFF_TOR, self.D_COEFF_TOR = co.P_COEFF_TOR, co.I_COEFF_TOR, co.D_COEFF_TOR
         self.PWM2RPM_SCALE, self.PWM2RPM_CONST, self.MIN_PWM, self.MAX_PWM = 0.2685, 4070.3, 20000, 65535
-        self._state = torch.zeros((9, self.num_drones), dtype=torch.float32, device=self.device)
+        self._state = torch.zeros((9, self.num_drones), dtype=torch.float64, device=self.device)
         n = self.num_drones
         f32 = dict(dtype=torch.float32, device=self.device)
         self._rpm, self._pos_e, self._yaw_e = torch.zeros((n, 4), **f32), torch.zeros((n, 3), **f32), torch.zeros((n,), **f32)
@@ -67,7 +67,7 @@ class DSLPIDControl(BaseControl):
     def set_state(self, integral_pos_e=None, last_rpy=None, integral_rpy_e=None):
         for k, a in ((0, integral_pos_e), (3, last_rpy), (6, integral_rpy_e)):
             if a is not None:
-                self._state[k:k + 3] = torch.as_tensor(np.asarray(a, dtype=np.float32).reshape(self.num_drones, 3).T.copy(), device=self.device)
+                self._state[k:k + 3] = torch.as_tensor(np.asarray(a, dtype=np.float64).reshape(self.num_drones, 3).T.copy(), device=self.device)
 
     def _dev(self, x, width, allow_none=False):
         """-> (contiguous float32 device tensor [n, width] or strided view, row stride in floats)."""

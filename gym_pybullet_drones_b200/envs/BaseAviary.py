@@ -3,7 +3,7 @@
 Keeps the constructor, attribute names, template-method hooks and reset/step
 surface of the reference's `BaseAviary` (gym_pybullet_drones/envs/BaseAviary.py:25-383)
 but owns no PyBullet client: the per-drone state is a structure of arrays of
-float32 CUDA tensors and `step()` is one call into the C-ABI CUDA library
+float64 CUDA tensors and `step()` is one call into the C-ABI CUDA library
 (include/quadsim.h).  Every `Physics` member runs the explicit `Physics.DYN`
 model (BaseAviary.py:815-892); the PYB_* members switch on the corresponding
 DYN+ aerodynamic terms.
@@ -201,13 +201,13 @@ class BaseAviary(Env):
         raise ValueError("[ERROR] invalid %s in BaseAviary.__init__(), try %s.reshape(NUM_DRONES,3)" % (name, name))
 
     def _table(self, arr, width=3):
-        """[D,w] or [E,D,w] float64 -> float32 device table [rows,4] (16-byte rows)."""
+        """[D,w] or [E,D,w] float64 -> float64 device table [rows,4] (32-byte rows)."""
         a = np.asarray(arr, dtype=np.float64)
         if self._tables_per_env:
             a = np.broadcast_to(a, (self._E, self._D, a.shape[-1])).reshape(self._N, a.shape[-1])
         else:
             a = a.reshape(self._D, a.shape[-1])
-        out = np.zeros((a.shape[0], 4), np.float32)
+        out = np.zeros((a.shape[0], 4), np.float64)
         out[:, :a.shape[1]] = a
         return torch.from_numpy(out).to(self.device)
 
@@ -220,12 +220,16 @@ class BaseAviary(Env):
         if raw and self._act_type() != N.ACT_RAW_RPM:
             self._flags |= N.FLAG_OBS_STATE20
         f32 = dict(dtype=torch.float32, device=dev)
-        self._planes = torch.zeros((4, n, 4), **f32)
-        self._last_rpm = torch.zeros((n, 4), **f32)
+        f64 = dict(dtype=torch.float64, device=dev)
+        #### persistent state, float64 (include/quadsim.h: QsState): [pos|w.x] [quat] [vel|w.y] planes of [n,4] + w.z [n] ####
+        self._planes = torch.zeros((13 * n,), **f64)
+        self._plane = self._planes[:12 * n].view(3, n, 4)
+        self._wz = self._planes[12 * n:]
+        self._last_rpm = torch.zeros((n, 4), **f64)
         self._step_counter = torch.zeros((E,), dtype=torch.int32, device=dev)
         self._pending = torch.zeros((E,), dtype=torch.uint8, device=dev)
         needs_pid = self._act_type() in (N.ACT_PID, N.ACT_VEL, N.ACT_ONE_D_PID)
-        self._pid = torch.zeros((9, n), **f32) if needs_pid else None
+        self._pid = torch.zeros((9, n), **f64) if needs_pid else None
         self._obs_buf = [torch.zeros((n, self._obs_dim), **f32), torch.zeros((n, self._obs_dim), **f32)]
         self._cur = 0
         self._reward = torch.zeros((E,), **f32)
@@ -235,6 +239,7 @@ class BaseAviary(Env):
         self._final_obs = torch.zeros((n, self._obs_dim), **f32) if (self._flags & N.FLAG_AUTORESET_SAME_STEP) else None
         big_dw = (self._effects & N.EFFECT_DW) and (D > 128 or self._EXTERNAL_DOWNWASH)
         self._dw_fz = torch.zeros((n,), **f32) if big_dw else None
+        self._pos_f32 = torch.zeros((n, 4), **f32) if big_dw else None                       # float32 position mirror (pair kernels)
         self._dw_boxes = torch.zeros((E, (D + 31) // 32, 8), **f32) if big_dw else None     # chunk boxes (qs_downwash_boxed)
         self._action_dev = torch.zeros((n, self._A), **f32)
         #### tables ####
@@ -254,6 +259,7 @@ class BaseAviary(Env):
         st.pid = self._pid.data_ptr() if self._pid is not None else None
         st.init_pos, st.init_quat = self._init_pos.data_ptr(), self._init_quat.data_ptr()
         st.target_pos = self._target.data_ptr() if self._target is not None else None
+        st.pos_f32 = self._pos_f32.data_ptr() if self._pos_f32 is not None else None
         st.tables_per_env = 1 if self._tables_per_env else 0
         self._st = st
         io = N.QsStepIO()
@@ -316,21 +322,19 @@ class BaseAviary(Env):
 
     @property
     def pos(self):
-        return self._planes[0, :, 0:3].view(self._E, self._D, 3) if self.VECTORIZED else self._host(self._planes[0, :, 0:3])
+        return self._plane[0, :, 0:3].view(self._E, self._D, 3) if self.VECTORIZED else self._host(self._plane[0, :, 0:3])
 
     @property
     def quat(self):
-        return self._planes[1].view(self._E, self._D, 4) if self.VECTORIZED else self._host(self._planes[1])
+        return self._plane[1].view(self._E, self._D, 4) if self.VECTORIZED else self._host(self._plane[1])
 
     @property
     def vel(self):
-        return self._planes[2, :, 0:3].view(self._E, self._D, 3) if self.VECTORIZED else self._host(self._planes[2, :, 0:3])
+        return self._plane[2, :, 0:3].view(self._E, self._D, 3) if self.VECTORIZED else self._host(self._plane[2, :, 0:3])
 
     @property
     def rpy_rates(self):
-        w = torch.stack([self._planes[0, :, 3].double() + self._planes[3, :, 1].double(),
-                         self._planes[2, :, 3].double() + self._planes[3, :, 2].double(),
-                         self._planes[3, :, 0].double() + self._planes[3, :, 3].double()], dim=1)
+        w = torch.stack([self._plane[0, :, 3], self._plane[2, :, 3], self._wz], dim=1)
         return w.view(self._E, self._D, 3) if self.VECTORIZED else w.cpu().numpy()
 
     @property
@@ -345,23 +349,29 @@ class BaseAviary(Env):
     def _host(t):
         return t.detach().cpu().numpy().astype(np.float64)
 
+    @property
+    def pid_state(self):
+        """[9, E*D] float64 CUDA tensor of the embedded controllers (integral_pos_e, last_rpy, integral_rpy_e) or None."""
+        return self._pid
+
     def set_state(self, pos=None, quat=None, vel=None, rpy_rates=None, step_counter=None):
-        """Overwrites (parts of) the kinematic state; arrays are [E,D,k] / [D,k] (any float dtype).
-        `rpy_rates` given as float64 keeps its extended precision."""
+        """Overwrites (parts of) the kinematic state; arrays are [E,D,k] / [D,k] (stored as float64)."""
         def dev(a, k):
+            if isinstance(a, torch.Tensor):
+                return a.to(device=self.device, dtype=torch.float64).reshape(self._N, k)
             return torch.as_tensor(np.asarray(a, dtype=np.float64).reshape(self._N, k), device=self.device)
         if pos is not None:
-            self._planes[0, :, 0:3] = dev(pos, 3).float()
+            self._plane[0, :, 0:3] = dev(pos, 3)
+            if self._pos_f32 is not None:
+                self._pos_f32[:, 0:3] = self._plane[0, :, 0:3].float()
         if quat is not None:
-            self._planes[1] = dev(quat, 4).float()
+            self._plane[1] = dev(quat, 4)
         if vel is not None:
-            self._planes[2, :, 0:3] = dev(vel, 3).float()
+            self._plane[2, :, 0:3] = dev(vel, 3)
         if rpy_rates is not None:
             w = dev(rpy_rates, 3)
-            hi = w.float()
-            lo = (w - hi.double()).float()
-            self._planes[0, :, 3], self._planes[2, :, 3], self._planes[3, :, 0] = hi[:, 0], hi[:, 1], hi[:, 2]
-            self._planes[3, :, 1], self._planes[3, :, 2], self._planes[3, :, 3] = lo[:, 0], lo[:, 1], lo[:, 2]
+            self._plane[0, :, 3], self._plane[2, :, 3] = w[:, 0], w[:, 1]
+            self._wz[:] = w[:, 2]
         if step_counter is not None:
             self._step_counter[:] = torch.as_tensor(np.broadcast_to(np.asarray(step_counter), (self._E,)).astype(np.int32), device=self.device)
 
@@ -439,9 +449,9 @@ class BaseAviary(Env):
                 self._downwash_stage(stream)
                 if raw:
                     last = s == S - 1
-                    rpm_src = io.action if s == 0 else self._last_rpm.data_ptr()
-                    rc = L.qs_dyn_substeps(C.byref(self._P), C.byref(self._st), rpm_src, io.obs if last else None,
-                                           self._dw_fz.data_ptr(), self._E, self._D, 1, self._effects, self._flags, stream)
+                    fl = self._flags | (N.FLAG_RPM_FROM_LAST if s > 0 else 0)      # substeps 1.. re-read the clipped rpm of substep 0
+                    rc = L.qs_dyn_substeps(C.byref(self._P), C.byref(self._st), io.action if s == 0 else None, io.obs if last else None,
+                                           self._dw_fz.data_ptr(), self._E, self._D, 1, self._effects, fl, stream)
                 else:
                     fl = self._flags | (N.FLAG_RPM_FROM_LAST if s > 0 else 0) | (N.FLAG_SKIP_EPILOGUE if s < S - 1 else 0)
                     io.tick_substeps = S
@@ -595,7 +605,7 @@ class BaseAviary(Env):
 
     def _getDroneStateVectors(self):
         """[E, D, 20] float64 ndarray of _getDroneStateVector (BaseAviary.py:541-561), computed from the state planes."""
-        pos, quat, vel = (self._planes[0, :, 0:3].double(), self._planes[1].double(), self._planes[2, :, 0:3].double())
+        pos, quat, vel = self._plane[0, :, 0:3], self._plane[1], self._plane[2, :, 0:3]
         x, y, z, w = quat[:, 0], quat[:, 1], quat[:, 2], quat[:, 3]
         sarg = -2.0 * (x * z - w * y)
         roll = torch.atan2(2.0 * (y * z + w * x), w * w - x * x - y * y + z * z)
@@ -604,7 +614,7 @@ class BaseAviary(Env):
         rpy = torch.stack([roll, pitch, yaw], dim=1)
         obs = self._obs_buf[self._cur]
         ang_v = obs[:, 13:16].double() if self._obs_dim == 20 else obs[:, 9:12].double()
-        sv = torch.cat([pos, quat, rpy, vel, ang_v, self._last_rpm.double()], dim=1)
+        sv = torch.cat([pos, quat, rpy, vel, ang_v, self._last_rpm], dim=1)
         return sv.view(self._E, self._D, 20).cpu().numpy()
 
     def _getDroneStateVector(self, nth_drone):

@@ -154,7 +154,7 @@ class FormationShard(CtrlAviary):
         L, sh = self._lib, self.shard
         if self.exchange == "local":
             return super()._downwash_stage(stream)
-        rows = self._planes[0]
+        rows = self._pos_f32          # float32 position mirror, refreshed by every substep kernel
         self._seq += 1
         buf = self._gathered[self._seq & 1]
         if self.exchange == "p2p":

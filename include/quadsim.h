@@ -27,8 +27,9 @@
  *     returns; safe under CUDA-graph capture.
  *   - return value: 0 = ok; <0 = argument error (QS_ERR_*); >0 = cudaError_t of the launch.
  *     qs_last_error() gives a message for the last non-zero return on the calling thread.
- *   - arithmetic: state is stored as float32 in HBM and advanced in float64 registers
- *     (dtype "f64" compute / "f32" storage); see DESIGN.md.
+ *   - arithmetic: the persistent state is float64 in HBM and is advanced in float64 registers, like the
+ *     reference (numpy float64 + Bullet doubles); actions and observations are float32 (the reference casts its
+ *     observations to float32, BaseRLAviary.py:315).  See DESIGN.md.
  */
 #ifndef QUADSIM_H_
 #define QUADSIM_H_
@@ -37,7 +38,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 1
+#define QS_ABI_VERSION 2     /* 2: the persistent state (planes, last_rpm, pid, init/target tables) is float64 */
 
 /* drone models (utils/enums.py:3-9) */
 enum { QS_MODEL_CF2X = 0, QS_MODEL_CF2P = 1, QS_MODEL_RACE = 2 };
@@ -111,23 +112,26 @@ typedef struct QsParams {
     int pad_;
 } QsParams;
 
-/* Per-drone persistent state, structure of arrays, N = n_envs * drones_per_env drones.
- * planes: float[4][N][4], 16-byte aligned:
- *   plane 0 = {pos.x, pos.y, pos.z, w.x}   plane 1 = {q.x, q.y, q.z, q.w}  (Bullet order x,y,z,w)
- *   plane 2 = {vel.x, vel.y, vel.z, w.y}   plane 3 = {w.z, w_lo.x, w_lo.y, w_lo.z}
- * w = body rates (`rpy_rates`, BaseAviary.py:877).  w_lo = float32 residual of w (w = w_hi + w_lo, ~48-bit
- * storage in the three otherwise unused lanes: rounding of the body rates is what dominates attitude drift
- * against the float64 reference).  0 is always a valid value for w_lo. */
+/* Per-drone persistent state, structure of arrays of float64, N = n_envs * drones_per_env drones.
+ * planes: double[13*N], 32-byte aligned (every thread moves its 104 bytes with three 32-byte and one 8-byte access):
+ *   plane 0 = [N][4] {pos.x, pos.y, pos.z, w.x}   plane 1 = [N][4] {q.x, q.y, q.z, q.w}  (Bullet order x,y,z,w)
+ *   plane 2 = [N][4] {vel.x, vel.y, vel.z, w.y}   plane 3 = [N]    {w.z}                 (at planes + 12*N)
+ * w = body rates (`rpy_rates`, BaseAviary.py:877).  Round 1 stored float32 planes: the rounding of the stored
+ * quaternion alone cost 1e-5 of parity on tumbling drones ("precision"); float64 storage costs 40 more
+ * bytes per drone and direction and puts the kernels within 1e-12 of the float64 reference. */
 typedef struct QsState {
-    float* planes;                  /* [4][N][4] */
-    float* last_rpm;                /* [N][4] last_clipped_action (BaseAviary.py:372); nullable unless DRAG / RAW_RPM */
+    double* planes;                 /* [13*N], see above */
+    double* last_rpm;               /* [N][4] last_clipped_action (BaseAviary.py:372); nullable unless DRAG / RAW_RPM / split substeps */
     int* step_counter;              /* [E] physics steps since reset (BaseAviary.py:382) */
     unsigned char* pending_reset;   /* [E] NEXT_STEP autoreset latch; nullable otherwise */
-    float* pid;                     /* [9][N]: integral_pos_e xyz, last_rpy xyz, integral_rpy_e xyz
+    double* pid;                    /* [9][N]: integral_pos_e xyz, last_rpy xyz, integral_rpy_e xyz
                                        (DSLPIDControl.py:73-78); nullable unless a PID action type */
-    const float* init_pos;          /* [D or N][4] INIT_XYZS (xyz, pad)             BaseAviary.py:194-201 */
-    const float* init_quat;         /* [D or N][4] getQuaternionFromEuler(INIT_RPYS) BaseAviary.py:488 */
-    const float* target_pos;        /* [D or N][4] TARGET_POS (HoverAviary.py:51, MultiHoverAviary.py:71); nullable for QS_TASK_NONE */
+    const double* init_pos;         /* [D or N][4] INIT_XYZS (xyz, pad)             BaseAviary.py:194-201 */
+    const double* init_quat;        /* [D or N][4] getQuaternionFromEuler(INIT_RPYS) BaseAviary.py:488 */
+    const double* target_pos;       /* [D or N][4] TARGET_POS (HoverAviary.py:51, MultiHoverAviary.py:71); nullable for QS_TASK_NONE */
+    float* pos_f32;                 /* optional [N][4] float32 mirror of the positions {x, y, z, 0}, refreshed by every kernel that
+                                       stores the state: the input of the float32 pairwise downwash kernels (qs_downwash*,
+                                       qs_dw_publish); nullable otherwise */
     int tables_per_env;             /* 0: the three tables have D rows shared by all envs; 1: N rows */
     int pad_;
 } QsState;
@@ -220,21 +224,22 @@ int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int 
                int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream);
 int qs_rollout_max_ticks(int act_type, int act_buffer_size, int drones_per_env);
 
-/* CtrlAviary semantics: rpm[N][4] clipped to [0, MAX_RPM], `substeps` x DYN, optional [N][20] state vectors. */
+/* CtrlAviary semantics: rpm[N][4] (float32) clipped to [0, MAX_RPM], `substeps` x DYN, optional [N][20] state vectors.
+ * With QS_FLAG_RPM_FROM_LAST `rpm` is ignored and the rpm of the previous call is re-read from QsState.last_rpm. */
 int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, float* state20_out, const float* dw_fz,
                     int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream);
 
 /* DSLPIDControl.computeControl for n drones.  cur_pos/cur_quat/cur_vel are read with a row stride (in floats),
  * so they can point into [n][20] state vectors (strides 20; BaseControl.computeControlFromState) or packed arrays.
- * target_rpy/target_vel/target_rpy_rates may be NULL (= zeros, the reference defaults).  pid_state: float[9][n]. */
-int qs_pid_control(const QsParams* p, float* pid_state, double control_timestep,
+ * target_rpy/target_vel/target_rpy_rates may be NULL (= zeros, the reference defaults).  pid_state: double[9][n]. */
+int qs_pid_control(const QsParams* p, double* pid_state, double control_timestep,
                    const float* cur_pos, int pos_stride, const float* cur_quat, int quat_stride,
                    const float* cur_vel, int vel_stride,
                    const float* target_pos, const float* target_rpy, const float* target_vel, const float* target_rpy_rates,
                    int n, float* rpm_out, float* pos_e_out, float* yaw_e_out, void* stream);
 
 /* Pairwise downwash within each aviary: fz_out[n] = sum over drones i of the same aviary with dz>0, dxy<10 of
- * -alpha*exp(-.5 (dxy/beta)^2) (force along n's body z).  Reads positions from the state planes. */
+ * -alpha*exp(-.5 (dxy/beta)^2) (force along n's body z).  Reads the float32 position mirror QsState.pos_f32. */
 int qs_downwash(const QsParams* p, const QsState* st, int n_envs, int drones_per_env, float* fz_out, void* stream);
 
 /* Downwash with a workspace: like qs_downwash, but first tabulates the bounding boxes of every 32 consecutive drones

@@ -1,35 +1,32 @@
 // TEST INFRASTRUCTURE: compiles gym_pybullet_drones_b200/csrc/quad_core.cuh (the per-drone math of the CUDA
 // kernels) as plain host C++ so the `-m "not gpu"` suite can check the same source against the oracle before
-// any GPU time is spent.  It reproduces the kernel's register/HBM precision split: float32 planes (with the
-// hi/lo body-rate lanes) loaded into float64, one control tick, stored back as float32.
+// any GPU time is spent.  It keeps the kernel's state layout: float64 planes ([pos|w.x] [quat] [vel|w.y] of [n][4], then
+// w.z [n]) loaded into registers, one control tick, quaternion renormalised, stored back.
 // Never linked into or imported by the product package.
 #include <cmath>
 #include <cstring>
 #include "../../gym_pybullet_drones_b200/csrc/quad_core.cuh"
 
 namespace {
-void load(const float* planes, long long N, long long i, qs::Drone& d) {
-    const float* p0 = planes + 4 * i; const float* p1 = planes + 4 * (N + i);
-    const float* p2 = planes + 4 * (2 * N + i); const float* p3 = planes + 4 * (3 * N + i);
+void load(const double* planes, long long N, long long i, qs::Drone& d) {
+    const double* p0 = planes + 4 * i; const double* p1 = planes + 4 * (N + i); const double* p2 = planes + 4 * (2 * N + i);
     d.px = p0[0]; d.py = p0[1]; d.pz = p0[2];
     d.qx = p1[0]; d.qy = p1[1]; d.qz = p1[2]; d.qw = p1[3];
     d.vx = p2[0]; d.vy = p2[1]; d.vz = p2[2];
-    d.wx = (double)p0[3] + (double)p3[1]; d.wy = (double)p2[3] + (double)p3[2]; d.wz = (double)p3[0] + (double)p3[3];
+    d.wx = p0[3]; d.wy = p2[3]; d.wz = planes[12 * N + i];
 }
-void split2(double v, float& hi, float& lo) { hi = (float)v; lo = (float)(v - (double)hi); }
-void store(float* planes, long long N, long long i, qs::Drone& d) {
+void store(double* planes, long long N, long long i, qs::Drone& d) {
     const double inv = 1.0 / std::sqrt(d.qx * d.qx + d.qy * d.qy + d.qz * d.qz + d.qw * d.qw);
     d.qx *= inv; d.qy *= inv; d.qz *= inv; d.qw *= inv;
-    float* p0 = planes + 4 * i; float* p1 = planes + 4 * (N + i); float* p2 = planes + 4 * (2 * N + i); float* p3 = planes + 4 * (3 * N + i);
-    float wxl, wyl, wzl;
-    p0[0] = (float)d.px; p0[1] = (float)d.py; p0[2] = (float)d.pz; split2(d.wx, p0[3], wxl);
-    p1[0] = (float)d.qx; p1[1] = (float)d.qy; p1[2] = (float)d.qz; p1[3] = (float)d.qw;
-    p2[0] = (float)d.vx; p2[1] = (float)d.vy; p2[2] = (float)d.vz; split2(d.wy, p2[3], wyl);
-    split2(d.wz, p3[0], wzl); p3[1] = wxl; p3[2] = wyl; p3[3] = wzl;
+    double* p0 = planes + 4 * i; double* p1 = planes + 4 * (N + i); double* p2 = planes + 4 * (2 * N + i);
+    p0[0] = d.px; p0[1] = d.py; p0[2] = d.pz; p0[3] = d.wx;
+    p1[0] = d.qx; p1[1] = d.qy; p1[2] = d.qz; p1[3] = d.qw;
+    p2[0] = d.vx; p2[1] = d.vy; p2[2] = d.vz; p2[3] = d.wy;
+    planes[12 * N + i] = d.wz;
 }
 template <int EFF>
-void tick_all(const QsParams& P, float* planes, int n, const float* act, int A, int act_type, int substeps,
-              float* last_rpm, float* pid, double* rec) {
+void tick_all(const QsParams& P, double* planes, int n, const float* act, int A, int act_type, int substeps,
+              double* last_rpm, double* pid, double* rec) {
     for (long long i = 0; i < n; ++i) {
         qs::Drone d; load(planes, n, i, d);
         float a[4] = {0, 0, 0, 0};
@@ -45,9 +42,9 @@ void tick_all(const QsParams& P, float* planes, int n, const float* act, int A, 
         qs::dyn_tick<EFF>(P, d, rpm, rpm_prev, 0.0, substeps, R);
         qs::Derived o; qs::derive<false>(d, R, o);
         store(planes, n, i, d);
-        for (int k = 0; k < 4; ++k) last_rpm[4 * i + k] = (float)rpm[k];
-        if (pid) { pid[i] = (float)ps.ipx; pid[n + i] = (float)ps.ipy; pid[2 * n + i] = (float)ps.ipz; pid[3 * n + i] = (float)ps.lr;
-                   pid[4 * n + i] = (float)ps.lp; pid[5 * n + i] = (float)ps.ly; pid[6 * n + i] = (float)ps.irx; pid[7 * n + i] = (float)ps.iry; pid[8 * n + i] = (float)ps.irz; }
+        for (int k = 0; k < 4; ++k) last_rpm[4 * i + k] = rpm[k];
+        if (pid) { pid[i] = ps.ipx; pid[n + i] = ps.ipy; pid[2 * n + i] = ps.ipz; pid[3 * n + i] = ps.lr;
+                   pid[4 * n + i] = ps.lp; pid[5 * n + i] = ps.ly; pid[6 * n + i] = ps.irx; pid[7 * n + i] = ps.iry; pid[8 * n + i] = ps.irz; }
         if (rec) {
             double* r = rec + i * 23;
             r[0] = d.px; r[1] = d.py; r[2] = d.pz; r[3] = d.qx; r[4] = d.qy; r[5] = d.qz; r[6] = d.qw;
@@ -61,8 +58,8 @@ void tick_all(const QsParams& P, float* planes, int n, const float* act, int A, 
 
 extern "C" {
 // one control tick for n independent drones; rec = [n][23] float64 (pos3 quat4 rpy3 vel3 ang_v3 w3 rpm4) or NULL
-void hh_tick(const QsParams* P, float* planes, int n, const float* act, int A, int act_type, int substeps, unsigned effects,
-             float* last_rpm, float* pid, double* rec) {
+void hh_tick(const QsParams* P, double* planes, int n, const float* act, int A, int act_type, int substeps, unsigned effects,
+             double* last_rpm, double* pid, double* rec) {
     switch (effects & 3u) {
         case 0: tick_all<0>(*P, planes, n, act, A, act_type, substeps, last_rpm, pid, rec); break;
         case 1: tick_all<1>(*P, planes, n, act, A, act_type, substeps, last_rpm, pid, rec); break;

@@ -3,12 +3,17 @@ against (a) golden vectors of the unmodified reference, (b) the float64 NumPy or
 finishes in seconds, (c) size-independent properties at BASELINE.json's full sizes.
 
 Tolerance (north star): |a - b| <= 1e-5 * max(|b|, 1) element-wise on the kinematic state over 1000 physics steps
-(RTOL).  Quaternions are compared up to sign."""
+(RTOL).  Quaternions are compared up to sign.  The state planes are float64 since round 2, so pos/quat/vel/rpy_rates
+are held to TIGHT (1e-9) wherever the reference trajectory itself is not chaotic; rpy and ang_v are read back from the
+float32 observation (the reference casts its observations to float32 too) and get OBS_TOL = 5e-7."""
 import numpy as np
 import pytest
 import torch
 
-from qs_testlib import FIELDS, RTOL, quat_err, relerr
+from qs_testlib import FIELDS, RTOL, TIGHT, quat_err, relerr
+
+OBS_TOL = 5e-7          # float32 cast of the observation (6e-8 rel) + atan2f/asinf on float64 arguments (2e-7 rad)
+OBS_FIELDS = ("rpy", "ang_v")
 
 pytestmark = pytest.mark.gpu
 
@@ -24,8 +29,8 @@ def _imports():
 def state_of(env):
     """float64 host copies of the kinematic state [E,D,.] + the derived rpy/ang_v of the last observation."""
     obs = env._obs_buf[env._cur].view(env._E, env._D, env._obs_dim).double().cpu().numpy()
-    out = dict(pos=env.pos.double().cpu().numpy(), quat=env.quat.double().cpu().numpy(), vel=env.vel.double().cpu().numpy(),
-               rpy_rates=env.rpy_rates.cpu().numpy())
+    assert env._planes.dtype == torch.float64
+    out = dict(pos=env.pos.cpu().numpy(), quat=env.quat.cpu().numpy(), vel=env.vel.cpu().numpy(), rpy_rates=env.rpy_rates.cpu().numpy())
     if env._obs_dim == 20:
         out["rpy"], out["ang_v"] = obs[..., 7:10], obs[..., 13:16]
     else:
@@ -33,12 +38,12 @@ def state_of(env):
     return out
 
 
-def check_fields(st, g, key, t, tol=RTOL, env_idx=0):
+def check_fields(st, g, key, t, tol=TIGHT, env_idx=0):
     for f in FIELDS:
         ref = g[key + "_" + f][t]
         mine = st[f][env_idx]
         e = quat_err(mine, ref) if f == "quat" else relerr(mine, ref)
-        assert e <= tol, (key, f, t, e)
+        assert e <= (max(tol, OBS_TOL) if f in OBS_FIELDS else tol), (key, f, t, e)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -56,7 +61,7 @@ def test_config1_hover_1000_physics_steps(golden, cf, steps, stream):
     obs, _ = env.reset()
     assert relerr(obs[0].cpu().numpy(), g[key + "_obs0"]) < 1e-6
     acts = g[key + "_actions"]
-    tol = RTOL if stream != "const" else 1e-4
+    tol = TIGHT
     for t in range(min(steps, acts.shape[0])):
         a = torch.from_numpy(np.broadcast_to(acts[t], (3, 1, 4)).copy()).cuda()
         obs, rew, term, trunc, _ = env.step(a)
@@ -66,7 +71,7 @@ def test_config1_hover_1000_physics_steps(golden, cf, steps, stream):
         assert abs(float(rew[0]) - g[key + "_reward"][t]) < 1e-5
         assert bool(term[0]) == bool(g[key + "_terminated"][t]) and bool(trunc[0]) == bool(g[key + "_truncated"][t]), t
         if t % 50 == 0:
-            assert relerr(obs[0].cpu().numpy(), g[key + "_obs"][t // 50]) < tol
+            assert relerr(obs[0].cpu().numpy(), g[key + "_obs"][t // 50]) < OBS_TOL
 
 
 def test_learn_config_episode_single_env_api(golden):
@@ -101,11 +106,11 @@ def test_multihover_golden(golden, key, nd, act):
     for t in range(125):      # 1000 physics steps
         a = torch.from_numpy(np.broadcast_to(acts[t], (2,) + acts[t].shape).copy()).cuda()
         obs, rew, term, trunc, _ = env.step(a)
-        check_fields(state_of(env), g, key, t, RTOL, 1)
-        assert abs(float(rew[1]) - g[key + "_reward"][t]) < 2e-5 * max(1.0, abs(g[key + "_reward"][t]))
+        check_fields(state_of(env), g, key, t, TIGHT, 1)
+        assert abs(float(rew[1]) - g[key + "_reward"][t]) < 5e-7 * max(1.0, abs(g[key + "_reward"][t]))
         assert bool(term[1]) == bool(g[key + "_terminated"][t]) and bool(trunc[1]) == bool(g[key + "_truncated"][t]), t
         if t % 10 == 0:
-            assert relerr(obs[1].cpu().numpy(), g[key + "_obs"][t // 10]) < RTOL
+            assert relerr(obs[1].cpu().numpy(), g[key + "_obs"][t // 10]) < OBS_TOL
 
 
 @pytest.mark.parametrize("model", ["CF2P", "RACE"])
@@ -122,8 +127,9 @@ def test_ctrl_aviary_other_models(golden, model):
         obs, r, te, tr, _ = env.step(acts[t])
         ref = g[key + "_obs"][t]
         assert r == -1 and te is False and tr is False
-        assert relerr(obs[:, 0:3], ref[:, 0:3]) < 3e-5 and quat_err(obs[:, 3:7], ref[:, 3:7]) < 3e-5, t
-        assert relerr(obs[:, 7:16], ref[:, 7:16]) < 1e-4 and relerr(obs[:, 16:20], ref[:, 16:20]) < 1e-7, t
+        # the raw RPM enter the ABI as float32 (the golden used float64 rpm): 6e-8 relative on the thrust, integrated twice
+        assert relerr(obs[:, 0:3], ref[:, 0:3]) < RTOL and quat_err(obs[:, 3:7], ref[:, 3:7]) < RTOL, t
+        assert relerr(obs[:, 7:16], ref[:, 7:16]) < RTOL and relerr(obs[:, 16:20], ref[:, 16:20]) < 1e-7, t
 
 
 @pytest.mark.parametrize("model", ["CF2X", "CF2P"])
@@ -167,12 +173,12 @@ def test_rl_pid_teacher_forced_30hz(golden, key, nd, act):
         if t > 0:
             env.set_state(pos=g[key + "_pos"][t - 1], quat=g[key + "_quat"][t - 1], vel=g[key + "_vel"][t - 1],
                           rpy_rates=g[key + "_rpy_rates"][t - 1], step_counter=t * 8)
-            env._pid[0:3] = torch.from_numpy(g[key + "_pid_integral_pos_e"][t - 1].T.astype(np.float32)).cuda()
-            env._pid[3:6] = torch.from_numpy(g[key + "_pid_last_rpy"][t - 1].T.astype(np.float32)).cuda()
-            env._pid[6:9] = torch.from_numpy(g[key + "_pid_integral_rpy_e"][t - 1].T.astype(np.float32)).cuda()
+            env._pid[0:3] = torch.from_numpy(g[key + "_pid_integral_pos_e"][t - 1].T.copy()).cuda()
+            env._pid[3:6] = torch.from_numpy(g[key + "_pid_last_rpy"][t - 1].T.copy()).cuda()
+            env._pid[6:9] = torch.from_numpy(g[key + "_pid_integral_rpy_e"][t - 1].T.copy()).cuda()
         obs, rew, term, trunc, _ = env.step(torch.from_numpy(acts[t][None]).cuda())
-        check_fields(state_of(env), g, key, t, 2e-5)
-        assert abs(float(rew[0]) - g[key + "_reward"][t]) < 1e-4 and bool(trunc[0]) == bool(g[key + "_truncated"][t])
+        check_fields(state_of(env), g, key, t, 1e-7)
+        assert abs(float(rew[0]) - g[key + "_reward"][t]) < 1e-6 and bool(trunc[0]) == bool(g[key + "_truncated"][t])
 
 
 @pytest.mark.parametrize("key,nd,act", PID_CASES)
@@ -183,9 +189,9 @@ def test_rl_pid_trajectory_120hz(golden, key, nd, act):
     acts = g[key + "_actions"]
     for t in range(acts.shape[0]):
         obs, rew, term, trunc, _ = env.step(torch.from_numpy(acts[t][None]).cuda())
-        check_fields(state_of(env), g, key, t, 5e-5)
+        check_fields(state_of(env), g, key, t, RTOL)
         if t % 10 == 0:
-            assert relerr(obs[0].cpu().numpy(), g[key + "_obs"][t // 10]) < 5e-5
+            assert relerr(obs[0].cpu().numpy(), g[key + "_obs"][t // 10]) < RTOL
 
 
 def test_pid_circle_workload(golden):
@@ -206,8 +212,8 @@ def test_pid_circle_workload(golden):
             action = g["action"][t - 1]
         obs, _, _, _, _ = env.step(action)
         ref = g["obs"][t]
-        tol = 5e-5 if t <= 8 else 2e-5
-        assert relerr(obs[:, 0:3], ref[:, 0:3]) < tol and quat_err(obs[:, 3:7], ref[:, 3:7]) < tol and relerr(obs[:, 7:16], ref[:, 7:16]) < 10 * tol, t
+        tol = RTOL
+        assert relerr(obs[:, 0:3], ref[:, 0:3]) < tol and quat_err(obs[:, 3:7], ref[:, 3:7]) < tol and relerr(obs[:, 7:16], ref[:, 7:16]) < tol, t
         rpm, pe, ye = ctrl.computeControlFromState(env.CTRL_TIMESTEP, obs, g["target"][t], target_rpy=g["INIT_RPYS"])
         if t > 8:
             assert relerr(rpm, g["action"][t]) < 1e-4, t
@@ -228,8 +234,8 @@ def test_velocity_aviary_golden(golden):
         obs, r, te, tr, _ = env.step(acts[t])
         ref = g["obs"][t]
         assert r == -1 and te is False and tr is False
-        assert relerr(obs[:, 0:3], ref[:, 0:3]) < 2e-5 and quat_err(obs[:, 3:7], ref[:, 3:7]) < 2e-5, t
-        assert relerr(obs[:, 7:16], ref[:, 7:16]) < 1e-4 and relerr(obs[:, 16:20], ref[:, 16:20]) < 1e-4, t
+        assert relerr(obs[:, 0:3], ref[:, 0:3]) < RTOL and quat_err(obs[:, 3:7], ref[:, 3:7]) < RTOL, t
+        assert relerr(obs[:, 7:16], ref[:, 7:16]) < RTOL and relerr(obs[:, 16:20], ref[:, 16:20]) < RTOL, t
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -261,28 +267,28 @@ def _compare_with_oracle(env, ora, acts, tol, check_obs_every=5):
                 e = float(np.max(np.abs(st[f] - ref) * cosp / np.maximum(np.abs(ref), 1.0)))
             else:
                 e = relerr(st[f], ref)
-            assert e <= tol, (f, t, e)
-        assert relerr(rew.cpu().numpy(), o_rew) < 10 * tol
+            assert e <= (max(tol, OBS_TOL) if f in OBS_FIELDS else tol), (f, t, e)
+        assert relerr(rew.cpu().numpy(), o_rew) < max(tol, OBS_TOL)
         assert np.array_equal(term.cpu().numpy(), o_term), t
         # a truncation bound crossed within rounding distance of the threshold may legitimately flip: skip those envs
         clear = ~_borderline(ora)
         assert np.array_equal(trunc.cpu().numpy()[clear], o_trunc[clear]), t
         if t % check_obs_every == 0:
-            assert relerr(obs.cpu().numpy(), o_obs) < tol
+            assert relerr(obs.cpu().numpy(), o_obs) < max(tol, OBS_TOL)
 
 
 @pytest.mark.parametrize("act,A", [("RPM", 4), ("ONE_D_RPM", 1)])
 def test_config3_multihover_4096_vs_oracle(act, A):
-    """MultiHover, E=2048 x D=2 (4096 drones), random actions, 125 ticks x 8 substeps = 1000 physics steps.
-    Tolerance 5e-5: the worst of 4096 tumbling trajectories (|v| up to 20 m/s) is ~3x the single-trajectory bound of
-    config 1; the error is the float32 rounding of the stored velocity (3e-8 |v| per tick, measured: rpy_rates agree to 1e-13)."""
+    """MultiHover, E=2048 x D=2 (4096 drones), random actions, 125 ticks x 8 substeps = 1000 physics steps of tumbling
+    flight (|v| up to 20 m/s): with float64 state planes the kernel stays within 1e-9 of the float64 oracle (round 1,
+    float32 planes: 5e-5, all of it the rounding of the stored quaternion)."""
     _, _, _, MultiHoverAviary, ActionType, _, Physics, O = _imports()
     E, D, T = 2048, 2, 125
     rng = np.random.default_rng(123)
     acts = rng.uniform(-1, 1, (T, E, D, A)).astype(np.float32)
     env = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType[act], num_envs=E)
     ora = O.OracleAviary("multihover", E, D, act=act.lower())
-    _compare_with_oracle(env, ora, acts, 5e-5)
+    _compare_with_oracle(env, ora, acts, TIGHT)
 
 
 def test_config2_pid_4096_fixed_setpoints_vs_oracle():
@@ -295,7 +301,7 @@ def test_config2_pid_4096_fixed_setpoints_vs_oracle():
     acts = np.broadcast_to(sp, (T, E, 1, 3)).copy()
     env = HoverAviary(physics=Physics.DYN, act=ActionType.PID, pyb_freq=240, ctrl_freq=120, num_envs=E)
     ora = O.OracleAviary("hover", E, 1, act="pid", ctrl_freq=120)
-    _compare_with_oracle(env, ora, acts, 5e-5, check_obs_every=25)
+    _compare_with_oracle(env, ora, acts, RTOL, check_obs_every=25)
 
 
 @pytest.mark.parametrize("phys,eff", [("PYB_GND", 1), ("PYB_DRAG", 2), ("PYB_DW", 4), ("PYB_GND_DRAG_DW", 7)])
@@ -310,7 +316,7 @@ def test_dynplus_effects_vs_oracle(phys, eff):
     acts = (0.3 * rng.uniform(-1, 1, (T, E, D, 4))).astype(np.float32)
     env = MultiHoverAviary(num_drones=D, initial_xyzs=xyz, physics=Physics[phys], act=ActionType.RPM, num_envs=E)
     ora = O.OracleAviary("multihover", E, D, act="rpm", initial_xyzs=xyz, effects=eff)
-    _compare_with_oracle(env, ora, acts, 2e-5)
+    _compare_with_oracle(env, ora, acts, 1e-7)
 
 
 def test_config4_big_formation_downwash_vs_oracle():
@@ -339,8 +345,8 @@ def test_config4_big_formation_downwash_vs_oracle():
         obs, _, _, _, _ = env.step(torch.from_numpy(a).cuda())
         o_obs, _, _, _ = ora.step(a)
         o = obs.cpu().numpy()
-        assert relerr(o[..., 0:3], o_obs[..., 0:3]) < 2e-5 and quat_err(o[..., 3:7], o_obs[..., 3:7]) < 2e-5, t
-        assert relerr(o[..., 7:16], o_obs[..., 7:16]) < 1e-4, t
+        assert relerr(o[..., 0:3], o_obs[..., 0:3]) < RTOL and quat_err(o[..., 3:7], o_obs[..., 3:7]) < RTOL, t
+        assert relerr(o[..., 7:16], o_obs[..., 7:16]) < RTOL, t
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -365,10 +371,10 @@ def test_autoreset_same_step_matches_manual_reset_loop():
         assert np.array_equal(info["_final_obs"].cpu().numpy(), done)
         if done.any():
             n_done += int(done.sum())
-            assert relerr(info["final_obs"].cpu().numpy()[done], o_obs[done]) < 2e-5
+            assert relerr(info["final_obs"].cpu().numpy()[done], o_obs[done]) < OBS_TOL
             o_obs2 = ora.reset(mask=done)
             o_obs = o_obs2
-        assert relerr(obs.cpu().numpy(), o_obs) < 2e-5, t
+        assert relerr(obs.cpu().numpy(), o_obs) < OBS_TOL, t
         assert np.array_equal(env.step_counter.cpu().numpy(), ora.step_counter), t
     assert n_done > E // 2      # random +-5 % RPM tips the drone past 0.4 rad quickly: plenty of resets exercised
 
@@ -400,8 +406,8 @@ def test_autoreset_next_step_semantics():
             o_obs_r = ora.reset(mask=pending)
             o_obs[pending] = o_obs_r[pending]
             o_rew[pending] = 0; o_term[pending] = False; o_trunc[pending] = False
-        assert relerr(obs.cpu().numpy(), o_obs) < 2e-5, t
-        assert relerr(rew.cpu().numpy(), o_rew) < 1e-4
+        assert relerr(obs.cpu().numpy(), o_obs) < OBS_TOL, t
+        assert relerr(rew.cpu().numpy(), o_rew) < OBS_TOL
         assert np.array_equal((term | trunc).cpu().numpy(), o_term | o_trunc), t
         pending = o_term | o_trunc
     assert saw > E // 4
@@ -448,11 +454,13 @@ def test_full_size_65536_properties():
         a = base[t].repeat(E // 64, 1, 1)           # aviary e gets stream e % 64
         obs, rew, term, trunc, _ = env.step(a)
     torch.cuda.synchronize()
-    q = env.quat.double()
+    q = env.quat
     assert torch.all(torch.isfinite(env._planes)) and torch.all(torch.isfinite(obs))
-    assert float((q.norm(dim=-1) - 1).abs().max()) < 2e-7
-    pl = env._planes.view(4, E // 64, 64, D, 4)
+    assert float((q.norm(dim=-1) - 1).abs().max()) < 1e-15
+    pl = env._plane.view(3, E // 64, 64, D, 4)
     assert torch.equal(pl[:, 0], pl[:, 1]) and torch.equal(pl[:, 0], pl[:, -1])
+    wz = env._wz.view(E // 64, 64, D)
+    assert torch.equal(wz[0], wz[1]) and torch.equal(wz[0], wz[-1])
     ob = obs.view(E // 64, 64, D, -1)
     assert torch.equal(ob[0], ob[-1]) and torch.equal(rew.view(-1, 64)[0], rew.view(-1, 64)[-1])
     o1, _ = env.reset(); p1 = env._planes.clone()
@@ -511,7 +519,7 @@ def test_ragged_aviary_sizes_vs_oracle(D, E, phys, eff):
     acts = (0.5 * rng.uniform(-1, 1, (T, E, D, 4))).astype(np.float32)
     env = MultiHoverAviary(num_drones=D, initial_xyzs=xyz, physics=Physics[phys], act=ActionType.RPM, num_envs=E)
     ora = O.OracleAviary("multihover", E, D, act="rpm", initial_xyzs=xyz, effects=eff)
-    _compare_with_oracle(env, ora, acts, 2e-5)
+    _compare_with_oracle(env, ora, acts, 1e-7)
 
 
 def test_set_pid_coefficients_changes_the_controller():
@@ -576,13 +584,13 @@ def test_autoreset_can_clear_action_buffer_and_controllers(mode):
         done = o_term | o_trunc
         assert np.array_equal((term | trunc).cpu().numpy(), done), t
         if mode == "same_step" and done.any():
-            assert relerr(info["final_obs"].cpu().numpy()[done], o_obs[done]) < 5e-5
+            assert relerr(info["final_obs"].cpu().numpy()[done], o_obs[done]) < RTOL
             clear(done)
             o_obs = ora.reset(mask=done)
             assert np.all(obs.cpu().numpy()[done][..., 12:] == 0)
         n_resets += int(done.sum())
-        assert relerr(obs.cpu().numpy(), o_obs) < 5e-5, t
+        assert relerr(obs.cpu().numpy(), o_obs) < RTOL, t
         pending = done if mode == "next_step" else pending
     assert n_resets > E // 2
-    pid_dev = env._pid.view(9, E).double().cpu().numpy()
-    assert relerr(pid_dev[0:3].T, ora.ctrl.integral_pos_e) < 1e-4 and relerr(pid_dev[6:9].T, ora.ctrl.integral_rpy_e) < 1e-3
+    pid_dev = env._pid.view(9, E).cpu().numpy()
+    assert relerr(pid_dev[0:3].T, ora.ctrl.integral_pos_e) < RTOL and relerr(pid_dev[6:9].T, ora.ctrl.integral_rpy_e) < 1e-4

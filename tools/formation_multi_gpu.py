@@ -151,11 +151,11 @@ def run(args, rank, world, local):
 
             def publish_only():
                 env._seq += 1
-                N.check(L.qs_dw_publish(env._planes[0].data_ptr(), sh.count, sh.start, env._gathered_ptrs[env._seq & 1], env.N_TOTAL,
+                N.check(L.qs_dw_publish(env._pos_f32.data_ptr(), sh.count, sh.start, env._gathered_ptrs[env._seq & 1], env.N_TOTAL,
                                         env._flag_ptrs, sh.world, sh.rank, env._seq, env._counter.data_ptr(), sp), "qs_dw_publish")
             res["part_us_publish_kernel"] = timed(publish_only)
         if mode == "nccl":
-            rows, buf = env._planes[0], env._gathered[0]
+            rows, buf = env._pos_f32, env._gathered[0]
             pos_view = buf[:4 * env.N_TOTAL].view(env.N_TOTAL, 4)
             res["part_us_nccl_all_gather"] = timed(lambda: env._all_gather_positions(rows, pos_view))
             res["part_us_boxes_kernel"] = timed(lambda: N.check(L.qs_dw_boxes(buf.data_ptr(), env.N_TOTAL, sp), "boxes"))
