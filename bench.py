@@ -10,10 +10,13 @@ step), random actions in [-1,1], SAME_STEP autoreset (an RL rollout).  One "step
 the fused kernel over all 65536 drones of the rank.  The working set of one batch (42 MB) fits the 126 MB L2, so the
 timed loop rotates over R independent batches (R x 42 MB > L2): every launch finds its inputs in HBM.
 
-JSON keys follow the driver contract; `value` = device-resident steps (actions already in HBM), `e2e` = the same
-steps through the NumPy API (pinned H2D of the actions + D2H of obs/reward/flags inside the timed region),
-`roofline` = algorithmic bytes of the step kernel / its mean launch duration (CUDA events around each launch)
-against MEASURED_PEAKS.json, `cpu_baseline` = the float64 NumPy oracle on a bounded sample on this host.
+JSON keys follow the driver contract; `value` = device-resident steps (actions already in HBM; the K-step window is
+repeated until >= 50 ms have been timed and the median window is reported, per-rank values alongside), `e2e` = the same
+steps through the NumPy API (pinned H2D of the actions + D2H of obs/reward/flags/terminal observations inside the timed
+region) with the pinned D2H copy rate measured in the same run (`pcie_frac`), `roofline` = algorithmic bytes of the step
+kernel / its launch period in the timed loop (`frac`, back-to-back launches overlap through programmatic dependent
+launch) and / its duration alone on an idle GPU with a cold L2 (`frac_isolated`), against MEASURED_PEAKS.json;
+`cpu_baseline` = the float64 NumPy oracle on a bounded sample on this host.
 """
 import argparse
 import json
@@ -46,7 +49,37 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batches", type=int, default=8, help="independent 65536-drone batches rotated through (L2 defeat)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--min-ms", type=float, default=50.0, help="repeat the K-step window until this much device time has been timed")
     return ap.parse_args()
+
+
+def bind_to_gpu_numa(local):
+    """Pins this process to the cores next to its GPU (sysfs local_cpulist of the PCI device) BEFORE any pinned memory is
+    allocated, so the staging buffers are first-touched on the GPU's NUMA node.  Returns a short description or None."""
+    try:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local
+        out = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout
+        bus = None
+        for line in out.strip().splitlines():
+            i, b = [c.strip() for c in line.split(",")]
+            if int(i) == phys:
+                bus = b
+        if bus is None:
+            return None
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/local_cpulist" % (dom[-4:].lower(), rest.lower())
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "gpu %d (%s) -> %d cores %s" % (phys, bus, len(cpus), open(path).read().strip())
+    except Exception:
+        return None
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -168,13 +201,14 @@ def main():
     if a.impl == "reference":
         reference_arm(a)
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa(local)
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -210,58 +244,106 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_gather_f(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world == 1:
+            return [float(x)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     def run(n, k0=0):
         for k in range(n):
             i = (k0 + k) % R
             envs[i].step(acts[i])
 
-    # ---- device-resident throughput --------------------------------------------------------------------------
-    run(a.warmup)
-    barrier()
+    # ---- device-resident throughput: windows of exactly K steps, barrier + sync on both sides, max over ranks per window ----
+    run(max(a.warmup, 3))
+    windows, total_ms, k0 = [], 0.0, a.warmup
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        ev0.record()
-        run(a.steps, a.warmup)
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
+        while (total_ms < a.min_ms or not windows) and len(windows) < 2000:
+            barrier()
+            ev0.record()
+            run(a.steps, k0)
+            ev1.record()
+            barrier()
+            w = all_max(ev0.elapsed_time(ev1))
+            windows.append(w)
+            total_ms += w
+            k0 += a.steps
         # keep the sampler over a little more load so short runs still see clocks under load
         t_end = time.time() + 0.6
         while time.time() < t_end:
             run(50)
         torch.cuda.synchronize()
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = DRONES_PER_GPU * world * a.steps / (ms_max * 1e-3)
+    ms_window = statistics.median(windows)
+    value = DRONES_PER_GPU * world * a.steps / (ms_window * 1e-3)
+    my_ms = []      # this rank's own windows (not max-reduced) for the per-rank report
+    for _ in range(min(len(windows), 20)):
+        torch.cuda.synchronize()
+        ev0.record()
+        run(a.steps, k0)
+        ev1.record()
+        torch.cuda.synchronize()
+        my_ms.append(ev0.elapsed_time(ev1))
+        k0 += a.steps
+    per_rank = all_gather_f(DRONES_PER_GPU * a.steps / (statistics.median(my_ms) * 1e-3))
 
-    # ---- per-launch kernel time for the roofline (events around every launch, L2-cold thanks to the rotation) ---
-    kt = []
-    n_k = min(a.steps, 400)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k)]
-    torch.cuda.synchronize()
-    for k in range(n_k):
-        i = k % R
-        evs[k][0].record()
-        envs[i].step(acts[i])
-        evs[k][1].record()
-    torch.cuda.synchronize()
-    kt = [s.elapsed_time(e) for s, e in evs]
-    kern_ms = statistics.mean(kt)
+    # ---- roofline of the step kernel: launch period in the timed loop (pipelined) and duration alone (isolated, cold L2) ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = ALG_BYTES * DRONES_PER_GPU / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": None, "kernel": "step_kernel<0,false>", "kernel_ms": kern_ms, "kernel_ms_median": statistics.median(kt),
-                "alg_bytes_per_drone_step": ALG_BYTES, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)"}
+    n_long = max(a.steps, 1000)
+    torch.cuda.synchronize()
+    ev0.record()
+    run(n_long, k0)
+    ev1.record()
+    torch.cuda.synchronize()
+    kern_ms = ev0.elapsed_time(ev1) / n_long                 # back-to-back launches of only this kernel: launch period
+    k0 += n_long
+    scrub = torch.empty(192 << 20, dtype=torch.uint8, device=dev)
+    iso = []
+    for k in range(40):
+        scrub.fill_(k & 255)                                  # evict the 126 MB L2
+        torch.cuda.synchronize()
+        ev0.record()
+        envs[k % R].step(acts[k % R])
+        ev1.record()
+        torch.cuda.synchronize()
+        iso.append(ev0.elapsed_time(ev1))
+    del scrub
+    iso_ms = statistics.median(iso)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_step_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    alg = ALG_BYTES * DRONES_PER_GPU
+    roofline = {"bound": "hbm", "achieved": alg / (kern_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                "frac": alg / (kern_ms * 1e-3) / 1e9 / peak_gbs, "frac_isolated": alg / (iso_ms * 1e-3) / 1e9 / peak_gbs,
+                "traffic": traffic, "kernel": "step_fast_kernel<A=4,task,reset,rpy_f32>", "kernel_ms": kern_ms, "kernel_ms_isolated": iso_ms,
+                "alg_bytes_per_drone_step": ALG_BYTES, "alg_bytes_per_launch": alg,
+                "timing": "frac: CUDA events around %d back-to-back launches / count (launch period; neighbours overlap through programmatic "
+                          "dependent launch); frac_isolated: median of events around single launches after a sync and a 192 MB L2 scrub "
+                          "(includes ~2 us of event/launch gap); traffic: ncu dram__bytes_read+write per launch (profiles/)" % n_long,
+                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)"}
 
-    # ---- end to end through the NumPy API: pinned H2D of actions, D2H of obs/reward/flags in the timed region ----
-    h_acts = [x.cpu().numpy() for x in acts]
+    # ---- end to end through the NumPy API: page-locked ndarray actions in, ndarrays out, every copy inside step() ----
+    h_acts = []
+    for x in acts:
+        t = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+        t.copy_(x)
+        h_acts.append(t.numpy())
     e2e_steps = max(10, min(a.steps, 200))
     for k in range(5):
         envs[k % R].step(h_acts[k % R])
@@ -271,17 +353,78 @@ def main():
         i = k % R
         obs, rew, term, trunc, info = envs[i].step(h_acts[i])
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = DRONES_PER_GPU * world * e2e_steps / float(t.item())
+    e2e_s = all_max(time.perf_counter() - t0)
+    e2e_val = DRONES_PER_GPU * world * e2e_steps / e2e_s
+    n_fin = int(info["final_obs"].shape[0]) if "final_obs" in info else 0
     h2d = DRONES_PER_GPU * A * 4
-    d2h = DRONES_PER_GPU * OBS_DIM * 4 + E * (4 + 1 + 1)
+    d2h = DRONES_PER_GPU * OBS_DIM * 4 + E * (4 + 1 + 1 + 1) + n_fin * (D * OBS_DIM * 4 + 8) + 4
+    # the link itself, same process, same pinned memory: one 19 MB device -> pinned host copy, repeated
+    hbuf = torch.empty((DRONES_PER_GPU, OBS_DIM), dtype=torch.float32).pin_memory()
+    dbuf = envs[0]._obs_buf[0]
+    for _ in range(3):
+        hbuf.copy_(dbuf, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        hbuf.copy_(dbuf, non_blocking=True)
+    torch.cuda.synchronize()
+    pcie_gbs = 20 * hbuf.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    e2e_gbs = (h2d + d2h) * e2e_steps / (e2e_s) / 1e9 if world == 1 else (h2d + d2h) / (DRONES_PER_GPU / (e2e_val / world)) / 1e9
+    e2e = {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "ms_per_step": 1e3 * e2e_s / e2e_steps, "d2h_gbs": d2h / (e2e_s / e2e_steps) / 1e9, "pcie_d2h_gbs_measured": pcie_gbs,
+           "pcie_frac": d2h / (e2e_s / e2e_steps) / 1e9 / pcie_gbs, "terminal_obs_aviaries_last_step": n_fin, "numa_binding": numa,
+           "api": "MultiHoverAviary.step(page-locked ndarray) -> ndarrays (qs_step_host: H2D actions, tick, device-side compaction of the "
+                  "finished aviaries, D2H obs/reward/flags + their terminal observations; host_copy=False)"}
+    del hbuf
 
-    # ---- extras (reported, not the headline): CUDA-graph replay of the same steps, and the host-side cost of a step ----
+    extras = {} if a.no_extras else run_extras(a, envs, acts, gen, dev, world, R, peak_gbs, barrier)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_window / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(a, DRONES_PER_GPU * world),
+            "clocks": clk.summary(),
+            "e2e": e2e,
+            "gpu_launches": a.steps * len(windows),
+            "timed_windows": {"count": len(windows), "steps_each": a.steps, "total_ms": total_ms, "ms_min": min(windows), "ms_median": ms_window, "ms_max": max(windows)},
+            "per_rank_value": per_rank,
+            "roofline": roofline,
+            "substeps_per_s": value * S,
+            "state_storage": "f64 planes (pos, quat, vel, body rates), f32 observations/actions; arithmetic f64",
+            "extras": extras,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_single()
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(a, envs, acts, gen, dev, world, R, peak_gbs, barrier):
+    """Reported next to the headline, never instead of it."""
+    import torch
+    from gym_pybullet_drones_b200.envs import HoverAviary, MultiHoverAviary
+    from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
     extras = {}
-    try:
+
+    def timed(fn, n, reps=3):
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            fn(n)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / n)
+        return best
+
+    def run(n):
+        for k in range(n):
+            envs[k % R].step(acts[k % R])
+
+    try:   # the same launches replayed from a CUDA graph: no per-step host work
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -293,84 +436,61 @@ def main():
             run(2 * R)                      # two ticks per batch: the obs double buffers end where they started
         for _ in range(3):
             g.replay()
-        barrier()
-        reps = max(1, min(a.steps, 2000) // (2 * R))
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(reps):
-            g.replay()
-        g1.record()
-        torch.cuda.synchronize()
-        gms = g0.elapsed_time(g1) / (reps * 2 * R)
+        gms = timed(lambda n: [g.replay() for _ in range(n)], 40) / (2 * R)
         extras["cuda_graph_replay"] = {"ms_per_step": gms, "value": DRONES_PER_GPU * world / (gms * 1e-3), "unit": METRIC,
-                                       "note": "same kernel launches captured once in a CUDA graph (16 steps per replay): no per-step host work"}
+                                       "hbm_frac": ALG_BYTES * DRONES_PER_GPU / (gms * 1e-3) / 1e9 / peak_gbs}
     except Exception as ex:  # pragma: no cover
         extras["cuda_graph_replay"] = {"error": repr(ex)}
-    if "ms_per_step" in extras.get("cuda_graph_replay", {}):
-        gms = extras["cuda_graph_replay"]["ms_per_step"]
-        timing = "CUDA events around K back-to-back graph-captured launches / K"
-        if ms / a.steps < gms:      # the plain timed loop (PDL launches, also back to back) bounds the kernel duration as well
-            gms, timing = ms / a.steps, "CUDA events around the K back-to-back launches of the timed region / K"
-        if gms < roofline["kernel_ms"]:
-            # back-to-back launches of ONLY this kernel inside one CUDA graph: elapsed/K bounds the kernel duration from
-            # above without the ~3 us of event/launch gap that per-launch event pairs include
-            roofline.update(kernel_ms_event_pairs=roofline["kernel_ms"], kernel_ms=gms,
-                            achieved=ALG_BYTES * DRONES_PER_GPU / (gms * 1e-3) / 1e9,
-                            frac=ALG_BYTES * DRONES_PER_GPU / (gms * 1e-3) / 1e9 / peak_gbs,
-                            timing=timing)
-    # the same kernel at sizes where several waves overlap load, compute and store (one batch, working set > L2)
+        torch.cuda.synchronize()
+    # the same kernel at sizes where several waves overlap load, compute and store (working set > L2)
     sweep = {}
     if world == 1:
         for n in (262144, 1048576):
             try:
-                big = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=n // D, device=dev, autoreset="same_step")
+                big = [MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=n // D, device=dev, autoreset="same_step") for _ in range(2)]
                 ba = torch.rand((n // D, D, A), device=dev, generator=gen) * 2 - 1
-                big.reset()
-                for _ in range(10):
-                    big.step(ba)
-                torch.cuda.synchronize()
-                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                b0.record()
-                for _ in range(100):
-                    big.step(ba)
-                b1.record()
-                torch.cuda.synchronize()
-                bms = b0.elapsed_time(b1) / 100
+                for b in big:
+                    b.reset()
+                bms = timed(lambda m: [big[k & 1].step(ba) for k in range(m)], 60)
                 sweep[str(n)] = {"ms_per_step": bms, "value": n / (bms * 1e-3), "hbm_frac": ALG_BYTES * n / (bms * 1e-3) / 1e9 / peak_gbs}
                 del big, ba
             except Exception as ex:  # pragma: no cover
                 sweep[str(n)] = {"error": repr(ex)}
         extras["drones_per_launch_sweep"] = sweep
-    # two of the rotating batches in flight at once (even batches on one stream, odd ones on another): how much of the
-    # one-wave launch latency independent batches can hide.  Reported only; the headline keeps one batch at a time.
+    # learn.py's default action type: ONE_D_RPM (A=1, obs 27 floats): 286 algorithmic bytes per drone-step
+    try:
+        e1 = [MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.ONE_D_RPM, num_envs=DRONES_PER_GPU // D, device=dev, autoreset="same_step") for _ in range(R)]
+        a1 = [torch.rand((DRONES_PER_GPU // D, D, 1), device=dev, generator=gen) * 2 - 1 for _ in range(R)]
+        for e in e1:
+            e.reset()
+        ms1 = timed(lambda m: [e1[k % R].step(a1[k % R]) for k in range(m)], 400)
+        alg1 = 52 + 52 + 4 + 4 * 14 + 4 + 4 * 27 + 4 + 2 + 4
+        extras["one_d_rpm_65536"] = {"ms_per_step": ms1, "value": DRONES_PER_GPU / (ms1 * 1e-3), "alg_bytes_per_drone_step": alg1,
+                                     "hbm_frac": alg1 * DRONES_PER_GPU / (ms1 * 1e-3) / 1e9 / peak_gbs}
+        del e1, a1
+    except Exception as ex:  # pragma: no cover
+        extras["one_d_rpm_65536"] = {"error": repr(ex)}
+    # two of the rotating batches in flight at once (even batches on one stream, odd ones on another)
     try:
         if R % 2 == 0:
             s_even, s_odd = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
             cur = torch.cuda.current_stream(dev)
 
             def run2(n):
+                s_even.wait_stream(cur)
+                s_odd.wait_stream(cur)
                 for k in range(n):
                     i = k % R
                     with torch.cuda.stream(s_even if (i & 1) == 0 else s_odd):
                         envs[i].step(acts[i])
+                cur.wait_stream(s_even)
+                cur.wait_stream(s_odd)
 
-            torch.cuda.synchronize()
             run2(64)
-            torch.cuda.synchronize()
-            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            nrep = max(64, min(a.steps, 1000))
-            q0.record(cur)
-            s_even.wait_stream(cur)
-            s_odd.wait_stream(cur)
-            run2(nrep)
-            cur.wait_stream(s_even)
-            cur.wait_stream(s_odd)
-            q1.record(cur)
-            torch.cuda.synchronize()
-            ms2 = q0.elapsed_time(q1) / nrep
+            ms2 = timed(run2, 400)
             extras["two_batches_in_flight"] = {"ms_per_step": ms2, "value": DRONES_PER_GPU * world / (ms2 * 1e-3), "unit": METRIC,
                                                "hbm_frac": ALG_BYTES * DRONES_PER_GPU / (ms2 * 1e-3) / 1e9 / peak_gbs,
-                                               "note": "same launches, even/odd batches on two streams (rank-local, not max over ranks)"}
+                                               "note": "same launches, even/odd batches on two streams (rank-local)"}
     except Exception as ex:  # pragma: no cover
         extras["two_batches_in_flight"] = {"error": repr(ex)}
         torch.cuda.synchronize()
@@ -380,22 +500,44 @@ def main():
         ro = None
         for k in range(3):
             ro = envs[0].rollout(num_steps=T, seed=7, out=ro)
-        torch.cuda.synchronize()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nrep = 20
-        r0.record()
-        for k in range(nrep):
-            ro = envs[k % R].rollout(num_steps=T, seed=7, out=ro)
-        r1.record()
-        torch.cuda.synchronize()
-        rms = r0.elapsed_time(r1) / (nrep * T)
+        hold = [ro]
+
+        def roll(n):
+            for k in range(n):
+                hold[0] = envs[k % R].rollout(num_steps=T, seed=7, out=hold[0])
+
+        rms = timed(roll, 20) / T
         extras["fused_rollout_T32"] = {"ms_per_step": rms, "value": DRONES_PER_GPU * world / (rms * 1e-3), "unit": METRIC,
                                        "hbm_frac_algorithmic": ALG_BYTES * DRONES_PER_GPU / (rms * 1e-3) / 1e9 / peak_gbs,
                                        "note": "qs_rollout: 32 control ticks per launch, state in registers, history in a sliding shared-memory window; "
                                                "per tick only the obs rows/reward/flags are written (the 646 B algorithmic figure counts traffic the fusion removes)"}
-        del ro
+        del ro, hold
     except Exception as ex:  # pragma: no cover
         extras["fused_rollout_T32"] = {"error": repr(ex)}
+    # BASELINE configs[1]: 4096 x HoverAviary with the embedded DSLPIDControl (act=PID): per-launch (launch-latency bound) and
+    # through the fused rollout, where the launch cost is paid once per 32 ticks
+    try:
+        pe = HoverAviary(physics=Physics.DYN, act=ActionType.PID, num_envs=4096, device=dev, autoreset="same_step")
+        pa = torch.rand((4096, 1, 3), device=dev, generator=gen) * torch.tensor([1.0, 1.0, 1.0], device=dev) + torch.tensor([-0.5, -0.5, 0.5], device=dev)
+        pe.reset()
+        msp = timed(lambda m: [pe.step(pa) for _ in range(m)], 400)
+        pacts = pa.unsqueeze(0).expand(32, -1, -1, -1).contiguous()
+        ro = pe.rollout(pacts)
+        hold = [ro]
+
+        def proll(n):
+            for _ in range(n):
+                hold[0] = pe.rollout(pacts, out=hold[0])
+
+        msr = timed(proll, 20) / 32
+        algp = 598
+        extras["config2_hover_pid_4096"] = {"per_launch_ms": msp, "per_launch_value": 4096 / (msp * 1e-3),
+                                            "rollout_T32_ms_per_tick": msr, "rollout_value": 4096 / (msr * 1e-3),
+                                            "alg_bytes_per_drone_step": algp, "rollout_hbm_frac": algp * 4096 / (msr * 1e-3) / 1e9 / peak_gbs,
+                                            "note": "2.4 MB per tick: launch-latency bound, not a bandwidth number"}
+        del pe, ro, hold
+    except Exception as ex:  # pragma: no cover
+        extras["config2_hover_pid_4096"] = {"error": repr(ex)}
     tiny = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=64, device=dev, autoreset="same_step")
     ta = torch.zeros((64, D, A), device=dev)
     tiny.reset()
@@ -407,26 +549,7 @@ def main():
         tiny.step(ta)
     torch.cuda.synchronize()
     extras["host_us_per_step_call"] = (time.perf_counter() - t0) / 2000 * 1e6
-
-    if rank == 0:
-        out = {
-            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(a, DRONES_PER_GPU * world),
-            "clocks": clk.summary(),
-            "e2e": {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "MultiHoverAviary.step(ndarray) -> ndarrays (pinned staging, host_copy=False)"},
-            "gpu_launches": a.steps,
-            "roofline": roofline,
-            "substeps_per_s": value * S,
-            "state_storage": "f32 planes (+f32 residual lanes for body rates); arithmetic f64",
-            "extras": extras,
-        }
-        if world == 1 and not a.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_single()
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    return extras
 
 
 if __name__ == "__main__":

@@ -53,7 +53,7 @@ class QsState(C.Structure):
     _fields_ = [
         ("planes", C.c_void_p), ("last_rpm", C.c_void_p), ("step_counter", C.c_void_p), ("pending_reset", C.c_void_p),
         ("pid", C.c_void_p), ("init_pos", C.c_void_p), ("init_quat", C.c_void_p), ("target_pos", C.c_void_p),
-        ("pos_f32", C.c_void_p), ("tables_per_env", C.c_int), ("pad_", C.c_int),
+        ("reset_head", C.c_void_p), ("pos_f32", C.c_void_p), ("tables_per_env", C.c_int), ("pad_", C.c_int),
     ]
 
 
@@ -75,7 +75,8 @@ class QsRolloutIO(C.Structure):
 
 class QsHostIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("action_host", "obs_host", "reward_host", "terminated_host", "truncated_host", "done_host",
-                                          "final_obs_host", "final_env_host", "n_final_host", "action_dev", "final_env_dev", "final_rows_dev")]
+                                          "final_obs_host", "final_env_host", "n_final_host", "action_dev", "final_env_dev", "n_final_dev",
+                                          "side_stream", "ev_fork", "ev_join")]
 
 
 class QsStepCall(C.Structure):
@@ -86,7 +87,7 @@ class QsStepCall(C.Structure):
 
 EXPORTS = ["qs_abi_version", "qs_last_error", "qs_sizeof_params", "qs_sizeof_state", "qs_sizeof_step_io",
            "qs_sizeof_rollout_io", "qs_sizeof_host_io", "qs_step", "qs_step_call", "qs_step_host", "qs_rollout", "qs_rollout_max_ticks", "qs_dyn_substeps", "qs_pid_control",
-           "qs_downwash", "qs_downwash_boxed", "qs_dw_gathered_floats", "qs_dw_boxes", "qs_downwash_rows", "qs_dw_publish", "qs_enable_peer_access", "qs_ipc_export", "qs_ipc_import", "qs_adjacency", "qs_reset"]
+           "qs_downwash", "qs_downwash_boxed", "qs_dw_gathered_floats", "qs_dw_boxes", "qs_downwash_rows", "qs_dw_publish", "qs_enable_peer_access", "qs_ipc_export", "qs_ipc_import", "qs_adjacency", "qs_reset", "qs_reset_heads", "qs_host_is_pinned"]
 MAX_PEERS = 16
 
 
@@ -149,6 +150,8 @@ def lib():
     L.qs_step_host.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.POINTER(QsStepIO), C.POINTER(QsHostIO), C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
     L.qs_sizeof_host_io.restype = C.c_int
+    L.qs_host_is_pinned.restype = C.c_int
+    L.qs_host_is_pinned.argtypes = [C.c_void_p]
     L.qs_rollout.restype = C.c_int
     L.qs_rollout.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.POINTER(QsRolloutIO), C.c_int, C.c_int,
                              C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
@@ -184,6 +187,8 @@ def lib():
     L.qs_ipc_import.argtypes = [C.c_void_p, C.c_ulonglong, C.POINTER(C.c_void_p)]
     L.qs_adjacency.restype = C.c_int
     L.qs_adjacency.argtypes = [C.POINTER(QsState), C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    L.qs_reset_heads.restype = C.c_int
+    L.qs_reset_heads.argtypes = [C.POINTER(QsState), C.c_int, C.c_uint, C.c_void_p, C.c_void_p]
     L.qs_reset.restype = C.c_int
     L.qs_reset.argtypes = [C.POINTER(QsParams), C.POINTER(QsState), C.c_void_p, C.c_int, C.c_int,
                            C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

@@ -43,6 +43,11 @@ struct StepArgs {
     unsigned effects, flags;
     int stage_rows;      // 1: the CTA's prev_obs rows are staged in shared memory by one TMA bulk copy
     int cap;             // CTA capacity in drones (64 or 128): sizes the shared-memory arrays
+    int log2D;           // log2(D) when D is a power of two, else -1
+    int sc_limit;        // smallest step counter with (double)sc / pyb_freq > episode_len_sec (HoverAviary.py:113)
+    int flags_late_tma;  // experiments (QS_LATE_TMA): 1 = issue the bulk copy only after the state loads have landed
+    int prefetch;        // experiments (QS_PREFETCH): 1 = L2 prefetch of the warp's inputs ahead of griddepcontrol.wait
+    int early_store;     // experiments (QS_EARLY_STORE): 1 = history written back as soon as it has landed (A = 4)
 };
 
 __device__ __forceinline__ float4 ldg4(const float* base, long long idx4) {
@@ -85,6 +90,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
+}
+
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {      // non-blocking
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
 __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src_gmem) {      // LDGSTS, 4-byte granule

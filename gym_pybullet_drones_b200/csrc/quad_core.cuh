@@ -171,9 +171,12 @@ QS_HD void integrate_q(Drone& d, double dt) {
 // rpm_prev = last_clipped_action: drag uses the previous tick's rpm in substep 0 and the current rpm
 // afterwards, because the reference refreshes last_clipped_action inside the substep loop (BaseAviary.py:372).
 // dw_fz = downwash force along body z for this substep (host launches one substep per call when DW is on).
-template <int EFF>
+// `between` is called after every substep with its index (the fused kernels poll an asynchronous copy there).
+struct NoHook { QS_HD void operator()(int) const {} };
+
+template <int EFF, class Hook = NoHook>
 QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const double rpm_prev[4], double dw_fz,
-                    int substeps, double R_last[9]) {
+                    int substeps, double R_last[9], Hook between = Hook()) {
     const double dt = P.dt;
     const double dt_m = dt * P.inv_m;                                                // v += dt * (F / M)  (:858,:860)
     double f[4];
@@ -268,6 +271,7 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
         d.py = d.py + dt * d.vy;
         d.pz = d.pz + dt * d.vz;
         integrate_q(d, dt);                                                          // :863
+        between(s);
     }
     quat_to_matrix(q0x, q0y, q0z, q0w, R_last);                                      // R used by :873 (ang_v = R_old w_new)
 }

@@ -99,13 +99,78 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ Rese
     }
 }
 
-// rows of the k finished aviaries -> compact buffer (one aviary = D*obs_dim contiguous floats)
-__global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, float* __restrict__ dst, int k, int row_floats) {
-    const int r = blockIdx.x;
-    if (r >= k) return;
-    const float* s = src + idx[r] * (long long)row_floats;
-    float* d = dst + (long long)r * row_floats;
-    for (int j = threadIdx.x; j < row_floats; j += blockDim.x) d[j] = s[j];
+__global__ void reset_heads_kernel(QsState st, int rows, int rpyf, float* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    qs::Drone d;
+    init_drone(st, r, d);
+    qs::Derived o;
+    const double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (rpyf) qs::derive<true>(d, R, o); else qs::derive<false>(d, R, o);
+    float* h = out + 12 * (long long)r;
+    h[0] = (float)d.px; h[1] = (float)d.py; h[2] = (float)d.pz;
+    h[3] = (float)o.roll; h[4] = (float)o.pitch; h[5] = (float)o.yaw;
+    h[6] = (float)d.vx; h[7] = (float)d.vy; h[8] = (float)d.vz;
+    h[9] = (float)o.ax; h[10] = (float)o.ay; h[11] = (float)o.az;
+}
+
+// Ascending indices of the finished aviaries (stream compaction of the done flags): one CTA of 1024 threads, a thread takes
+// 32 consecutive flags, block-wide exclusive scan of the counts, chunks of 32 768 flags in sequence.
+__global__ void __launch_bounds__(1024) compact_done_kernel(const unsigned char* __restrict__ done, int E, long long* __restrict__ idx, int* __restrict__ count) {
+    __shared__ int warp_tot[32];
+    __shared__ int chunk_tot;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int base = 0;
+    for (int c0 = 0; c0 < E; c0 += 1024 * 32) {
+        const int b = c0 + 32 * t;
+        unsigned mask = 0u;
+        if (b + 32 <= E && ((reinterpret_cast<uintptr_t>(done) + b) & 15u) == 0) {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(done + b), v1 = *reinterpret_cast<const uint4*>(done + b + 16);
+            const unsigned w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) if ((w[q] >> (8 * r)) & 0xffu) mask |= 1u << (4 * q + r);
+        } else {
+            for (int q = 0; q < 32; ++q) if (b + q < E && done[b + q]) mask |= 1u << q;
+        }
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+            warp_tot[lane] = wi - w;                                  // exclusive prefix of the warp totals
+            if (lane == 31) chunk_tot = wi;
+        }
+        __syncthreads();
+        int off = base + warp_tot[warp] + incl - cnt;
+        for (unsigned m = mask; m; m &= m - 1) idx[off++] = b + __ffs(m) - 1;
+        base += chunk_tot;
+        __syncthreads();
+    }
+    if (t == 0) *count = base;
+}
+
+// rows of the k finished aviaries (one aviary = D*obs_dim contiguous floats) -> compact array, indices and k alongside;
+// dst / idx_out / k_out may be mapped host memory (the stores then travel over PCIe next to the observation copy)
+__global__ void __launch_bounds__(128) gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, const int* __restrict__ count,
+                                                          float* __restrict__ dst, long long* __restrict__ idx_out, int* __restrict__ k_out, int row_floats) {
+    const int k = *count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *k_out = k;
+    const bool vec = (row_floats & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    for (int r = blockIdx.x; r < k; r += gridDim.x) {
+        const long long ev = idx[r];
+        if (threadIdx.x == 0) idx_out[r] = ev;
+        const float* s = src + ev * (long long)row_floats;
+        float* d = dst + (long long)r * row_floats;
+        if (vec) for (int j = threadIdx.x; j < (row_floats >> 2); j += blockDim.x) reinterpret_cast<float4*>(d)[j] = reinterpret_cast<const float4*>(s)[j];
+        else for (int j = threadIdx.x; j < row_floats; j += blockDim.x) d[j] = s[j];
+    }
 }
 
 }  // namespace
@@ -188,6 +253,21 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
     a.tpb = block_size_for(drones_per_env, a.cap);
     a.counter_inc = io->tick_substeps > 0 ? io->tick_substeps : substeps;
     a.effects = effects; a.flags = flags;
+    {
+        static const int late = getenv("QS_LATE_TMA") ? atoi(getenv("QS_LATE_TMA")) : 1;
+        static const int pre = getenv("QS_PREFETCH") ? atoi(getenv("QS_PREFETCH")) : 1;
+        static const int early = getenv("QS_EARLY_STORE") ? atoi(getenv("QS_EARLY_STORE")) : 1;
+        a.flags_late_tma = late; a.prefetch = pre; a.early_store = early;
+    }
+    a.log2D = -1;
+    for (int k = 0; k < 6; ++k) if ((1 << k) == drones_per_env) a.log2D = k;
+    {   // time-out threshold on the integer step counter, evaluated with the reference's float64 division
+        long long s = (long long)(p->episode_len_sec * p->pyb_freq) - 2;
+        if (s < 0) s = 0;
+        while (!((double)s / p->pyb_freq > p->episode_len_sec) && s < 0x7fffffffLL) ++s;
+        a.sc_limit = (int)s;
+    }
+    if (st->reset_head && !aligned16(st->reset_head)) return fail(QS_ERR_ALIGN, "qs_step: reset_head must be 16-byte aligned");
     // staging of the CTA's prev_obs rows in shared memory: TMA bulk copy when every CTA's span is 16-byte aligned and sized,
     // per-thread LDGSTS otherwise; none when the span does not fit (e.g. 240 Hz control: 120-action buffers)
     {
@@ -209,6 +289,13 @@ int qs_step_call(const QsStepCall* c, void* stream) {
     return qs_step(c->p, c->st, c->io, c->act_type, c->task, c->n_envs, c->drones_per_env, c->substeps, c->effects, c->flags, stream);
 }
 
+int qs_host_is_pinned(const void* p) {
+    if (!p) return 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return at.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const QsHostIO* h, int act_type, int task,
                  int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream) {
     if (!io || !h) return fail(QS_ERR_NULL, "qs_step_host: NULL io");
@@ -221,66 +308,55 @@ int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const
     const long long N = (long long)n_envs * drones_per_env;
     const int od = state20 ? 20 : 12 + io->act_buffer_size * A;
     const bool want_final = (flags & QS_FLAG_AUTORESET_SAME_STEP) && io->final_obs && h->final_obs_host;
-    if (want_final && (!io->done || !h->done_host || !h->final_env_host || !h->n_final_host || !h->final_env_dev || !h->final_rows_dev))
-        return fail(QS_ERR_NULL, "qs_step_host: final_obs transfer needs done / final_env / final_rows buffers");
+    if (want_final && (!io->done || !h->done_host || !h->final_env_host || !h->n_final_host || !h->final_env_dev || !h->n_final_dev))
+        return fail(QS_ERR_NULL, "qs_step_host: final_obs transfer needs done / final_env / n_final buffers");
+    if ((h->ev_fork == nullptr) != (h->ev_join == nullptr) || (h->side_stream && !h->ev_fork))
+        return fail(QS_ERR_NULL, "qs_step_host: side_stream needs ev_fork and ev_join");
     cudaStream_t s = (cudaStream_t)stream;
     static const bool trace = getenv("QS_TRACE") != nullptr;
     static int trace_n = 0;
     auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
     const double t0 = trace ? now() : 0.0;
-    double t1 = 0, t2 = 0, t3 = 0;
     cudaError_t e = cudaMemcpyAsync(h->action_dev, h->action_host, (size_t)N * A * 4, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return cuda_fail(e, "qs_step_host H2D action");
     QsStepIO dio = *io;
     dio.action = h->action_dev;
     if (int rc = qs_step(p, st, &dio, act_type, task, n_envs, drones_per_env, substeps, effects, flags, stream)) return rc;
-    volatile int* marker = want_final ? h->n_final_host : nullptr;
-    if (marker) *marker = -1;
+    bool forked = false;
+    if (want_final) {
+        // terminal observations: device-side compaction of the done flags (ascending), then the gather kernel writes the rows,
+        // their indices and the count into the mapped host arrays.  On a side stream this overlaps the copies below.
+        float* rows_h = nullptr; long long* idx_h = nullptr; int* k_h = nullptr;
+        if ((e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&rows_h), h->final_obs_host, 0)) != cudaSuccess ||
+            (e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&idx_h), h->final_env_host, 0)) != cudaSuccess ||
+            (e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&k_h), h->n_final_host, 0)) != cudaSuccess)
+            return cuda_fail(e, "qs_step_host: final_obs_host / final_env_host / n_final_host must be pinned, mapped host memory");
+        cudaStream_t fs = s;
+        if (h->side_stream && h->ev_fork) {
+            fs = (cudaStream_t)h->side_stream;
+            cudaEventRecord((cudaEvent_t)h->ev_fork, s);
+            cudaStreamWaitEvent(fs, (cudaEvent_t)h->ev_fork, 0);
+            forked = true;
+        }
+        compact_done_kernel<<<1, 1024, 0, fs>>>(io->done, n_envs, h->final_env_dev, h->n_final_dev);
+        const int row_floats = drones_per_env * od;
+        const int blocks = n_envs < 1184 ? n_envs : 1184;                                  // 148 SMs x 8, grid-stride over the k rows
+        gather_rows_kernel<<<blocks, 128, 0, fs>>>(io->final_obs, h->final_env_dev, h->n_final_dev, rows_h, idx_h, k_h, row_floats);
+        if (forked) cudaEventRecord((cudaEvent_t)h->ev_join, fs);
+    } else if (h->n_final_host) {
+        *h->n_final_host = 0;
+    }
     cudaMemcpyAsync(h->reward_host, io->reward, (size_t)n_envs * 4, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(h->terminated_host, io->terminated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(h->truncated_host, io->truncated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
     if (io->done && h->done_host) cudaMemcpyAsync(h->done_host, io->done, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
-    if (want_final) {
-        // The flags are 100 KB, the observations 19 MB.  A 4-byte copy queued behind the flag copies is their completion
-        // marker (n_final_host, preset to -1: no reward has that bit pattern); the observation copy is queued right
-        // after it, so it is in flight while the host waits for the marker, picks the finished aviaries and queues
-        // their rows behind it.
-        cudaMemcpyAsync(const_cast<int*>(marker), io->reward, 4, cudaMemcpyDeviceToHost, s);
-        cudaMemcpyAsync(h->obs_host, io->obs, (size_t)N * od * 4, cudaMemcpyDeviceToHost, s);
-        if (trace) t1 = now();
-        {
-            const double t_spin = now();
-            unsigned it = 0;
-            while (*marker == -1) {
-                if ((++it & 1023u) == 0 && now() - t_spin > 50000.0) {               // 50 ms: fall back to a full wait
-                    e = cudaStreamSynchronize(s);
-                    if (e != cudaSuccess) return cuda_fail(e, "qs_step_host sync(flags)");
-                    break;
-                }
-            }
-        }
-        __atomic_thread_fence(__ATOMIC_ACQUIRE);                  // the flag arrays are read after the marker
-        if (trace) t2 = now();
-        int k = 0;
-        for (int ev = 0; ev < n_envs; ++ev)
-            if (h->done_host[ev]) h->final_env_host[k++] = ev;
-        *h->n_final_host = k;
-        if (k > 0) {
-            const int row_floats = drones_per_env * od;
-            cudaMemcpyAsync(h->final_env_dev, h->final_env_host, (size_t)k * 8, cudaMemcpyHostToDevice, s);
-            gather_rows_kernel<<<k, 128, 0, s>>>(io->final_obs, h->final_env_dev, h->final_rows_dev, k, row_floats);
-            cudaMemcpyAsync(h->final_obs_host, h->final_rows_dev, (size_t)k * row_floats * 4, cudaMemcpyDeviceToHost, s);
-        }
-    } else {
-        if (h->n_final_host) *h->n_final_host = 0;
-        cudaMemcpyAsync(h->obs_host, io->obs, (size_t)N * od * 4, cudaMemcpyDeviceToHost, s);
-    }
-    if (trace) t3 = now();
+    cudaMemcpyAsync(h->obs_host, io->obs, (size_t)N * od * 4, cudaMemcpyDeviceToHost, s);
+    if (forked) cudaStreamWaitEvent(s, (cudaEvent_t)h->ev_join, 0);
+    const double t1 = trace ? now() : 0.0;
     e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return cuda_fail(e, "qs_step_host sync");
     if (trace && (++trace_n % 50) == 0)
-        fprintf(stderr, "[qs_step_host] enqueue1 %.0f us, sync(flags) %.0f us, scan+enqueue2 %.0f us, final sync %.0f us, n_final %d\n",
-                t1 - t0, t2 - t1, t3 - t2, now() - t3, h->n_final_host ? *h->n_final_host : -1);
+        fprintf(stderr, "[qs_step_host] enqueue %.0f us, sync %.0f us, n_final %d\n", t1 - t0, now() - t1, h->n_final_host ? *h->n_final_host : -1);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_step_host");
 }
@@ -329,6 +405,15 @@ int qs_pid_control(const QsParams* p, double* pid_state, double control_timestep
     pid_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_pid_control launch");
+}
+
+int qs_reset_heads(const QsState* st, int rows, unsigned flags, float* out, void* stream) {
+    if (!st || !st->init_pos || !st->init_quat || !out) return fail(QS_ERR_NULL, "qs_reset_heads: NULL argument");
+    if (!aligned32(st->init_pos) || !aligned32(st->init_quat) || !aligned16(out)) return fail(QS_ERR_ALIGN, "qs_reset_heads: misaligned table");
+    if (rows <= 0) return fail(QS_ERR_SIZE, "qs_reset_heads: rows must be > 0");
+    reset_heads_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*st, rows, (flags & QS_FLAG_RPY_F32) ? 1 : 0, out);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "qs_reset_heads launch");
 }
 
 int qs_reset(const QsParams* p, const QsState* st, const unsigned char* mask, int n_envs, int drones_per_env,

@@ -39,8 +39,19 @@ _AUTORESET = {None: 0, "disabled": 0, AUTORESET_DISABLED: 0,
               "same_step": N.FLAG_AUTORESET_SAME_STEP, AUTORESET_SAME_STEP: N.FLAG_AUTORESET_SAME_STEP}
 
 
+_TASK_HOOKS = ("_computeReward", "_computeTerminated", "_computeTruncated")
+
+
 class BaseAviary(Env):
-    """Base class for the GPU aviaries (reference: envs/BaseAviary.py:19)."""
+    """Base class for the GPU aviaries (reference: envs/BaseAviary.py:19).
+
+    Template-method seam (BaseAviary.py:1021-1104): the built-in envs evaluate `_preprocessAction`, `_computeObs`,
+    `_computeReward`, `_computeTerminated`, `_computeTruncated` inside the fused kernel.  A USER subclass that overrides
+    one of them is honoured: the kernel then only advances the physics (and writes the built-in observation), and the
+    overridden hooks run in Python after every tick on the device state (`pos`, `quat`, `vel`, `rpy_rates`,
+    `_getDroneStateVector(i)`, the built-in `super()._compute*()` values).  Single-env API: the hooks return what the
+    reference's hooks return.  Vector API: `_computeReward/_computeTerminated/_computeTruncated` return [E] arrays or
+    tensors; same-step autoreset is then carried out by the host side of the env."""
 
     metadata = {"render_modes": []}
     _EXTERNAL_DOWNWASH = False      # True: the downwash force always comes from `_downwash_stage` (sharded formations)
@@ -138,6 +149,21 @@ class BaseAviary(Env):
             self._flags |= N.FLAG_RPY_F32
         self.autoreset_mode = {0: AUTORESET_DISABLED, N.FLAG_AUTORESET_NEXT_STEP: AUTORESET_NEXT_STEP,
                                N.FLAG_AUTORESET_SAME_STEP: AUTORESET_SAME_STEP}[_AUTORESET[autoreset]]
+        #### hooks overridden by a user subclass (the built-in envs leave them to the kernel) ####
+        self._hook_task = [h for h in _TASK_HOOKS if self._user_override(h)]
+        self._hook_obs = self._user_override("_computeObs")
+        self._hook_pre = self._user_override("_preprocessAction")
+        self._py_hooks = bool(self._hook_task or self._hook_obs or self._hook_pre)
+        self._py_autoreset = False
+        if self._py_hooks:
+            if self._hook_pre and self._act_type() != N.ACT_RAW_RPM:
+                raise NotImplementedError("_preprocessAction can only be overridden on raw-RPM envs (CtrlAviary): the RL action "
+                                          "types are decoded inside the kernel, which also keeps the action buffer of the observation")
+            if self._flags & N.FLAG_AUTORESET_NEXT_STEP:
+                raise NotImplementedError("autoreset='next_step' is not available with Python task hooks; use 'same_step' or reset(options={'reset_mask': ...})")
+            if self._hook_task:      # the kernel must not reset on its own verdict: the host does it after the hooks ran
+                self._py_autoreset = bool(self._flags & N.FLAG_AUTORESET_SAME_STEP)
+                self._flags &= ~(N.FLAG_AUTORESET_SAME_STEP | N.FLAG_AUTORESET_NEXT_STEP)
         self.metadata = dict(self.metadata, autoreset_mode=self.autoreset_mode)
         self._host_copy = host_copy
         #### Initial poses (BaseAviary.py:194-207); [D,3] shared by all aviaries or [E,D,3] per aviary ####
@@ -163,6 +189,13 @@ class BaseAviary(Env):
 
     ################################################################################
     # configuration supplied by subclasses
+
+    def _user_override(self, name):
+        """True if the hook `name` is defined by a class outside this package, i.e. by a user subclass."""
+        for klass in type(self).__mro__:
+            if name in vars(klass):
+                return not klass.__module__.startswith(__name__.split(".envs.")[0] + ".")
+        return False
 
     def _act_type(self):
         """QS_ACT_* of this env (RAW_RPM for CtrlAviary-style envs)."""
@@ -262,6 +295,12 @@ class BaseAviary(Env):
         st.pos_f32 = self._pos_f32.data_ptr() if self._pos_f32 is not None else None
         st.tables_per_env = 1 if self._tables_per_env else 0
         self._st = st
+        #### observation head of a freshly reset drone, tabulated once on the device (SAME_STEP autoreset) ####
+        self._reset_head = torch.zeros((self._init_pos.shape[0], 12), **f32)
+        with self._on_device():
+            N.check(self._lib.qs_reset_heads(C.byref(st), self._init_pos.shape[0], self._flags, self._reset_head.data_ptr(),
+                                             self._stream()), "qs_reset_heads")
+        st.reset_head = self._reset_head.data_ptr()
         io = N.QsStepIO()
         io.reward, io.terminated, io.truncated = self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr()
         io.final_obs = self._final_obs.data_ptr() if self._final_obs is not None else None
@@ -274,7 +313,7 @@ class BaseAviary(Env):
         self._obs_ptr = [b.data_ptr() for b in self._obs_buf]
         self._obs_view = [b.view(E, D, self._obs_dim) for b in self._obs_buf]
         self._final_view = self._final_obs.view(E, D, self._obs_dim) if self._final_obs is not None else None
-        self._simple_launch = self._dw_fz is None and not raw and not self._state20_obs()
+        self._simple_launch = self._dw_fz is None and not raw and not self._state20_obs() and not self._py_hooks
         self._qs_step = self._lib.qs_step
         self._step_head = (C.byref(self._P), C.byref(self._st), C.byref(io), self._act_type(), self._task(),
                            E, D, self.PYB_STEPS_PER_CTRL, self._effects, self._flags)
@@ -285,7 +324,7 @@ class BaseAviary(Env):
         call.substeps, call.effects, call.flags = self.PYB_STEPS_PER_CTRL, self._effects, self._flags
         self._call, self._call_ptr, self._qs_step_call = call, C.addressof(call), self._lib.qs_step_call
         self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
-        #### pinned host staging for the NumPy API ####
+        #### pinned host staging for the NumPy API (double buffered: views stay valid until the next-but-one step) ####
         self._h_action = torch.zeros((n, self._A), dtype=torch.float32).pin_memory()
         self._h_obs = [torch.zeros((n, self._obs_dim), dtype=torch.float32).pin_memory() for _ in range(2)]
         self._h_reward = [torch.zeros((E,), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -293,29 +332,43 @@ class BaseAviary(Env):
         self._h_trunc = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
         self._hcur = 0
         self._h_done = [torch.zeros((E,), dtype=torch.bool).pin_memory() for _ in range(2)]
-        self._h_nfinal_t = torch.zeros((1,), dtype=torch.int32).pin_memory()      # also the flag-copy completion marker of qs_step_host
-        self._h_nfinal = self._h_nfinal_t.numpy()
-        self._h_idx = torch.zeros((E,), dtype=torch.int64).pin_memory()
+        self._h_nfinal = [torch.zeros((1,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._h_idx = [torch.zeros((E,), dtype=torch.int64).pin_memory() for _ in range(2)]
         self._idx_dev = torch.zeros((E,), dtype=torch.int64, device=dev)
+        self._nfinal_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self._h_final = None
         if self._final_obs is not None:
-            self._final_rows = torch.zeros((E, D, self._obs_dim), **f32)
-            self._h_final = torch.zeros((E, D, self._obs_dim), dtype=torch.float32).pin_memory()
+            self._h_final = [torch.zeros((E, D, self._obs_dim), dtype=torch.float32).pin_memory() for _ in range(2)]
+            # compaction + gather of the terminal observations run next to the observation copy (qs_step_host)
+            self._side_stream = torch.cuda.Stream(device=dev)
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+            with self._on_device():
+                self._ev_fork.record(); self._ev_join.record()          # materialise the cudaEvent_t handles
         self._h_action_np = self._h_action.numpy()
-        self._h_idx_np = self._h_idx.numpy()
-        self._h_final_np = self._h_final.numpy() if self._final_obs is not None else None
-        self._hio, self._h_np = [], []
+        self._h_action_view = self._h_action_np.reshape(E, D, self._A) if self.VECTORIZED else self._h_action_np.reshape(D, self._A)
+        self._h_action_ptr = self._h_action.data_ptr()
+        self._hio, self._h_np, self._h_fin_np = [], [], []
         for k in range(2):
             h = N.QsHostIO()
             h.action_host, h.obs_host = self._h_action.data_ptr(), self._h_obs[k].data_ptr()
             h.reward_host, h.terminated_host = self._h_reward[k].data_ptr(), self._h_term[k].data_ptr()
             h.truncated_host, h.done_host = self._h_trunc[k].data_ptr(), self._h_done[k].data_ptr()
-            h.final_env_host, h.n_final_host = self._h_idx.data_ptr(), self._h_nfinal.ctypes.data
-            h.action_dev, h.final_env_dev = self._action_dev.data_ptr(), self._idx_dev.data_ptr()
+            h.final_env_host, h.n_final_host = self._h_idx[k].data_ptr(), self._h_nfinal[k].data_ptr()
+            h.action_dev, h.final_env_dev, h.n_final_dev = self._action_dev.data_ptr(), self._idx_dev.data_ptr(), self._nfinal_dev.data_ptr()
             if self._final_obs is not None:
-                h.final_obs_host, h.final_rows_dev = self._h_final.data_ptr(), self._final_rows.data_ptr()
+                h.final_obs_host = self._h_final[k].data_ptr()
+                h.side_stream, h.ev_fork, h.ev_join = self._side_stream.cuda_stream, self._ev_fork.cuda_event, self._ev_join.cuda_event
             self._hio.append(h)
             self._h_np.append((self._h_obs[k].numpy().reshape(E, D, self._obs_dim), self._h_reward[k].numpy(),
                                self._h_term[k].numpy(), self._h_trunc[k].numpy()))
+            self._h_fin_np.append((self._h_nfinal[k].numpy(), self._h_idx[k].numpy(),
+                                   self._h_final[k].numpy() if self._h_final is not None else None))
+
+    def pinned_actions(self):
+        """float32 ndarray view ([E, D, A], or [D, A] for the single-env API) of the env's page-locked action buffer: fill it
+        and pass it to step() -- the H2D copy then starts from it directly, without the staging memcpy that an ordinary
+        ndarray needs.  Any other page-locked array (torch.empty(...).pin_memory().numpy()) is recognised as well."""
+        return self._h_action_view
 
     ################################################################################
     # state views (float32 CUDA tensors; names follow BaseAviary.py:470-476)
@@ -478,6 +531,8 @@ class BaseAviary(Env):
         Vector API: `action` is a float32 CUDA tensor [E, D, A] (used in place) or an ndarray (copied through a
         pinned buffer); returns tensors or ndarrays accordingly.  Single-env API: ndarray [D, A] in, the
         reference's 5-tuple out (BaseAviary.py:262-290)."""
+        if self._py_hooks:
+            return self._step_hooked(action)
         if type(action) is torch.Tensor and self.VECTORIZED and self._simple_launch:
             #### fast path: device tensor in, device tensors out, one kernel launch, no other device work ####
             a = action
@@ -549,8 +604,16 @@ class BaseAviary(Env):
         """One qs_step_host call: every host<->device copy of the tick happens inside the C library."""
         k = self._hcur
         self._hcur = 1 - k
-        self._h_action_np[...] = a_np
         io, cur, h = self._io, self._cur, self._hio[k]
+        ptr = a_np.ctypes.data
+        if ptr != self._h_action_ptr:
+            if a_np.flags.c_contiguous and self._lib.qs_host_is_pinned(ptr):
+                h.action_host = ptr                              # caller-owned page-locked array: no staging copy
+            else:
+                self._h_action_np[...] = a_np
+                h.action_host = self._h_action_ptr
+        else:
+            h.action_host = ptr
         io.obs_prev = self._obs_ptr[cur]
         io.obs = self._obs_ptr[1 - cur]
         rc = self._lib.qs_step_host(*self._step_head[:3], C.byref(h), *self._step_head[3:], torch.cuda.current_stream().cuda_stream)
@@ -560,16 +623,51 @@ class BaseAviary(Env):
         o, rew, term, trunc = self._h_np[k]
         info = {}
         if self._final_obs is not None:
-            nd = int(self._h_nfinal[0])
+            nf, idx, fin = self._h_fin_np[k]
+            nd = int(nf[0])
             info = {"_final_obs": term | trunc}
             if nd:
-                info["final_obs_env"] = self._h_idx_np[:nd]                      # indices of the finished aviaries
-                info["final_obs"] = self._h_final_np[:nd]                        # their terminal observations [k, D, obs_dim]
+                info["final_obs_env"] = idx[:nd]                                 # indices of the finished aviaries (ascending)
+                info["final_obs"] = fin[:nd]                                     # their terminal observations [k, D, obs_dim]
         if self._host_copy:
             o, rew, term, trunc = o.copy(), rew.copy(), term.copy(), trunc.copy()
             if "final_obs" in info:
                 info["final_obs"], info["final_obs_env"] = info["final_obs"].copy(), info["final_obs_env"].copy()
         return o, rew, term, trunc, info
+
+    def _step_hooked(self, action):
+        """step() when a user subclass overrides template-method hooks (BaseAviary.py:1021-1104): kernel tick, then the hooks."""
+        numpy_in = not isinstance(action, torch.Tensor)
+        with self._on_device():
+            if self._hook_pre:                                 # raw-RPM envs: action -> RPMs (CtrlAviary.py:121-140)
+                action = self._preprocessAction(action)
+            a = action if isinstance(action, torch.Tensor) else torch.as_tensor(np.asarray(action, dtype=np.float32))
+            a = a.to(device=self.device, dtype=torch.float32).reshape(self._N, self._A)
+            self._action_dev.copy_(a)
+            self._launch(self._action_dev)
+            obs = self._computeObs()
+            rew, term, trunc = self._computeReward(), self._computeTerminated(), self._computeTruncated()
+            if not self.VECTORIZED:
+                if isinstance(obs, torch.Tensor):
+                    obs = obs.detach().cpu().numpy()
+                to_f = lambda x: float(x.item()) if isinstance(x, torch.Tensor) else float(x)      # noqa: E731
+                to_b = lambda x: bool(x.item()) if isinstance(x, torch.Tensor) else bool(x)        # noqa: E731
+                return obs, to_f(rew), to_b(term), to_b(trunc), self._computeInfo()
+            dev = self.device
+            rew = torch.as_tensor(rew, device=dev).to(torch.float32).reshape(self._E)
+            term = torch.as_tensor(term, device=dev).to(torch.bool).reshape(self._E)
+            trunc = torch.as_tensor(trunc, device=dev).to(torch.bool).reshape(self._E)
+            info = {}
+            if self._py_autoreset:
+                done = term | trunc
+                info = {"final_obs": obs.clone() if isinstance(obs, torch.Tensor) else np.array(obs), "_final_obs": done}
+                if bool(done.any()):
+                    self._housekeeping(done.to(torch.uint8).contiguous())
+                    obs = self._computeObs()
+            if numpy_in:
+                cv = lambda x: x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x     # noqa: E731
+                return cv(obs), cv(rew), cv(term), cv(trunc), {k: cv(v) for k, v in info.items()}
+            return obs, rew, term, trunc, info
 
     def _single_result(self, obs):
         o = self._obs_to_host_single(obs)
@@ -642,6 +740,21 @@ class BaseAviary(Env):
 
     def _observationSpace(self):
         raise NotImplementedError
+
+    def _computeObs(self):
+        """Current observation, as the kernel wrote it (BaseAviary.py:1048-1056)."""
+        obs = self._obs_buf[self._cur]
+        return self._shape_obs(obs) if self.VECTORIZED else self._obs_to_host_single(obs)
+
+    def _computeReward(self):
+        """The kernel's reward of the last tick: [E] tensor, or a float for the single-env API (BaseAviary.py:1060-1068)."""
+        return self._reward if self.VECTORIZED else float(self._reward[0].item())
+
+    def _computeTerminated(self):
+        return self._terminated if self.VECTORIZED else bool(self._terminated[0].item())
+
+    def _computeTruncated(self):
+        return self._truncated if self.VECTORIZED else bool(self._truncated[0].item())
 
     def _computeInfo(self):
         return {"answer": 42}

@@ -129,6 +129,9 @@ typedef struct QsState {
     const double* init_pos;         /* [D or N][4] INIT_XYZS (xyz, pad)             BaseAviary.py:194-201 */
     const double* init_quat;        /* [D or N][4] getQuaternionFromEuler(INIT_RPYS) BaseAviary.py:488 */
     const double* target_pos;       /* [D or N][4] TARGET_POS (HoverAviary.py:51, MultiHoverAviary.py:71); nullable for QS_TASK_NONE */
+    const float* reset_head;        /* optional [D or N][12] float32: the kinematic head (pos3 rpy3 vel3 ang_v3) of the observation of a
+                                       freshly reset drone, filled once by qs_reset_heads; lets SAME_STEP autoreset take the leaner
+                                       kernels (without it the head is recomputed inside the tick: same values) */
     float* pos_f32;                 /* optional [N][4] float32 mirror of the positions {x, y, z, 0}, refreshed by every kernel that
                                        stores the state: the input of the float32 pairwise downwash kernels (qs_downwash*,
                                        qs_dw_publish); nullable otherwise */
@@ -174,7 +177,10 @@ typedef struct QsRolloutIO {
 } QsRolloutIO;
 
 /* Host-buffer variant of one control tick (what a CPU-side caller such as SB3's DummyVecEnv loop sees): pinned host
- * arrays in, pinned host arrays out, every host<->device copy inside the call. */
+ * arrays in, pinned host arrays out, every host<->device copy inside the call.  The terminal observations of the
+ * aviaries that finished (SAME_STEP autoreset) are compacted on the device (ascending aviary index) and written by the
+ * gather kernel straight into the pinned host arrays (mapped memory), so nothing waits for the host in the middle of
+ * the tick; with side_stream/ev_fork/ev_join they move concurrently with the copy of the observations. */
 typedef struct QsHostIO {
     const float* action_host;        /* [N][A]  (pinned) */
     float* obs_host;                 /* out [N][obs_dim] */
@@ -182,13 +188,20 @@ typedef struct QsHostIO {
     unsigned char* terminated_host;  /* out [E] */
     unsigned char* truncated_host;   /* out [E] */
     unsigned char* done_host;        /* out [E] */
-    float* final_obs_host;           /* out: rows [k][D][obs_dim] of the k aviaries that finished (SAME_STEP autoreset); nullable */
-    long long* final_env_host;       /* out [E]: their aviary indices, ascending (pinned; doubles as the upload staging) */
-    int* n_final_host;               /* out: k (pinned: it doubles as the completion marker of the flag copies) */
+    float* final_obs_host;           /* out: rows [k][D][obs_dim] of the k aviaries that finished (SAME_STEP autoreset); nullable.
+                                        Pinned AND mapped (cudaHostAlloc / cudaHostRegister): written by a kernel */
+    long long* final_env_host;       /* out [E]: their aviary indices, ascending (pinned, mapped) */
+    int* n_final_host;               /* out: k (pinned, mapped) */
     float* action_dev;               /* caller-owned device scratch [N][A] */
     long long* final_env_dev;        /* caller-owned device scratch [E] */
-    float* final_rows_dev;           /* caller-owned device scratch [E][D][obs_dim] */
+    int* n_final_dev;                /* caller-owned device scratch [1] */
+    void* side_stream;               /* optional cudaStream_t for the compaction + gather of the terminal observations */
+    void* ev_fork;                   /* optional cudaEvent_t pair (timing disabled) used to fork/join side_stream; both or neither */
+    void* ev_join;
 } QsHostIO;
+
+/* 1 if `p` points into page-locked host memory known to the CUDA driver (cudaHostAlloc / cudaHostRegister), else 0. */
+int qs_host_is_pinned(const void* p);
 
 int qs_abi_version(void);
 const char* qs_last_error(void);
@@ -278,6 +291,11 @@ int qs_enable_peer_access(int peer_device);
 /* BaseAviary._getAdjacencyMatrix (envs/BaseAviary.py:658-675) for every aviary: out[e][i][j] = 1 if i == j or
  * |pos_i - pos_j| < radius else 0 (unsigned char [E][D][D]). */
 int qs_adjacency(const QsState* st, int n_envs, int drones_per_env, double radius, unsigned char* out, void* stream);
+
+/* Fills `out` ([rows][12] float32, 16-byte aligned; rows = D or N like the init tables) with the observation head of a freshly
+ * reset drone: (float)INIT_XYZS, rpy of the initial quaternion (float32 atan2f/asinf iff flags has QS_FLAG_RPY_F32), zeros --
+ * exactly what the tick writes for an aviary it resets.  Point QsState.reset_head at it afterwards. */
+int qs_reset_heads(const QsState* st, int rows, unsigned flags, float* out, void* stream);
 
 /* Reset envs to their initial pose.  mask: [E] bytes, nullable = all envs.  Zeroes velocities, body rates,
  * last_rpm, step counter; with reset_pid != 0 also the PID state (the reference never does).

@@ -174,3 +174,106 @@ def test_rollout_device_action_generator():
     outb = e2.rollout(num_steps=5, seed=1234)
     b_ref = MultiHoverAviary.rollout_actions_reference(1234, T, 5, E * D, 4).reshape(5, E, D, 4)
     assert np.array_equal(outb["actions"].cpu().numpy(), b_ref)
+
+
+@pytest.mark.parametrize("cls,act,D,E,mode,rpy_f32", [
+    ("MultiHoverAviary", "RPM", 2, 1024, "same_step", True), ("MultiHoverAviary", "ONE_D_RPM", 2, 1024, "same_step", True),
+    ("HoverAviary", "RPM", 1, 333, "same_step", True), ("HoverAviary", "ONE_D_RPM", 1, 1000, None, False),
+    ("MultiHoverAviary", "RPM", 4, 77, "same_step", False), ("MultiHoverAviary", "RPM", 32, 5, None, True),
+    ("MultiHoverAviary", "ONE_D_RPM", 8, 300, "same_step", True)])
+def test_fast_step_kernels_are_bit_identical_to_the_general_kernel(cls, act, D, E, mode, rpy_f32, monkeypatch):
+    """step_fast.cu (warp-per-span kernels, templated on A / task / autoreset / rpy precision) against step_general.cu
+    (QS_FAST=0) on the same inputs: observations, rewards, flags, terminal observations, state planes and counters are equal
+    bit for bit, ragged last warps and 32-drone aviaries included."""
+    import gym_pybullet_drones_b200.envs as envs
+    from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
+    kw = dict(physics=Physics.DYN, act=ActionType[act], num_envs=E, autoreset=mode, rpy_f32=rpy_f32)
+    if cls == "MultiHoverAviary":
+        kw["num_drones"] = D
+    e1, e2 = getattr(envs, cls)(**kw), getattr(envs, cls)(**kw)
+    A = e1._A
+    g = torch.Generator(device="cuda").manual_seed(3)
+    e1.reset(); e2.reset()
+    n_done = 0
+    for t in range(150):
+        a = torch.rand((E, D, A), device="cuda", generator=g) * 2 - 1
+        monkeypatch.setenv("QS_FAST", "1")
+        o1, r1, te1, tr1, i1 = e1.step(a)
+        monkeypatch.setenv("QS_FAST", "0")
+        o2, r2, te2, tr2, i2 = e2.step(a)
+        for name, x, y in (("obs", o1, o2), ("reward", r1, r2), ("terminated", te1, te2), ("truncated", tr1, tr2), ("planes", e1._planes, e2._planes),
+                           ("step_counter", e1._step_counter, e2._step_counter), ("last_rpm", e1._last_rpm, e2._last_rpm)):
+            assert torch.equal(x, y), (name, t, float((x.double() - y.double()).abs().max()))
+        if mode == "same_step":
+            done = i1["_final_obs"]
+            assert torch.equal(done, i2["_final_obs"]) and torch.equal(i1["final_obs"][done], i2["final_obs"][done]), t
+            n_done += int(done.sum())
+    if mode == "same_step":
+        assert n_done > 0
+
+
+def test_user_subclass_hooks_are_honoured():
+    """The reference's template-method seam (BaseAviary.py:1021-1104): a user subclass overriding _computeReward /
+    _computeTruncated (single-env and vector API) and _preprocessAction (CtrlAviary) is called after every tick; the
+    kernel then only advances the physics.  Checked against the same quantities computed from the built-in env."""
+    from gym_pybullet_drones_b200.envs import CtrlAviary, HoverAviary
+    from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
+
+    class MyHover(HoverAviary):            # reference-style hooks (HoverAviary.py:68-117 rewritten by a user)
+        def _computeReward(self):
+            state = self._getDroneStateVector(0)
+            return -float(np.linalg.norm(self.TARGET_POS - state[0:3]))
+
+        def _computeTruncated(self):
+            return bool(self._getDroneStateVector(0)[2] > 0.2)
+
+    env, ref = MyHover(physics=Physics.DYN, act=ActionType.RPM), HoverAviary(physics=Physics.DYN, act=ActionType.RPM)
+    assert env._py_hooks and not ref._py_hooks
+    env.reset(); ref.reset()
+    saw_trunc = False
+    for t in range(40):
+        a = np.full((1, 4), 0.5, np.float32)
+        o, r, te, tr, info = env.step(a)
+        o2, r2, te2, tr2, _ = ref.step(a)
+        assert np.array_equal(o, o2) and info == {"answer": 42}
+        z = ref._getDroneStateVector(0)[2]
+        assert abs(r + np.linalg.norm(np.array([0, 0, 1.0]) - ref._getDroneStateVector(0)[0:3])) < 1e-12 and tr == bool(z > 0.2) and te == te2
+        saw_trunc |= tr
+    assert saw_trunc
+
+    class MyVecHover(HoverAviary):         # vector API: hooks return [E] tensors
+        def _computeReward(self):
+            return -(self.pos[:, 0, 2] - 1.0).abs().float()
+
+        def _computeTerminated(self):
+            return self.pos[:, 0, 2] > 0.15
+
+    E = 64
+    venv = MyVecHover(physics=Physics.DYN, act=ActionType.RPM, num_envs=E, autoreset="same_step")
+    obs, _ = venv.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n_done = 0
+    for t in range(60):
+        a = torch.rand((E, 1, 4), device="cuda", generator=g)
+        z_before = venv.pos[:, 0, 2].clone()
+        obs, r, te, tr, info = venv.step(a)
+        assert r.shape == (E,) and te.dtype == torch.bool and not bool(tr.any())
+        done = info["_final_obs"]
+        assert torch.equal(done, te)
+        # finished aviaries were reset by the host side: back at the initial height, terminal observation kept
+        assert torch.all(venv.pos[done][:, 0, 2] == venv.INIT_XYZS[0, 2]) and torch.all(info["final_obs"][done][:, 0, 2] > 0.15)
+        assert torch.all(venv.step_counter[done] == 0)
+        n_done += int(done.sum())
+    assert n_done > 0
+
+    class MyCtrl(CtrlAviary):              # CtrlAviary._preprocessAction (CtrlAviary.py:121-140) replaced: action = thrust fraction
+        def _preprocessAction(self, action):
+            return np.repeat(np.asarray(action, np.float64) * self.MAX_RPM, 4, axis=-1)
+
+    c, cref = MyCtrl(num_drones=2, physics=Physics.DYN), CtrlAviary(num_drones=2, physics=Physics.DYN)
+    c.reset(); cref.reset()
+    for t in range(20):
+        frac = np.array([[0.6], [0.7]])
+        o, *_ = c.step(frac)
+        o2, *_ = cref.step(np.repeat(frac * cref.MAX_RPM, 4, axis=-1))
+        assert np.array_equal(o, o2)
