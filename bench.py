@@ -235,7 +235,9 @@ def main():
     envs = [MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E, device=dev,
                              autoreset="same_step", host_copy=False) for _ in range(R)]
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    acts = [torch.rand((E, D, A), device=dev, generator=gen) * 2 - 1 for _ in range(R)]
+    # uniform[-1, 1) actions, a fresh draw every step: K_ACT action tensors per batch, cycled (8 x 16 x 1 MB)
+    K_ACT = 16
+    acts = [[torch.rand((E, D, A), device=dev, generator=gen) * 2 - 1 for _ in range(K_ACT)] for _ in range(R)]
     for e in envs:
         e.reset()
 
@@ -259,9 +261,9 @@ def main():
         return [float(o.item()) for o in out]
 
     def run(n, k0=0):
-        for k in range(n):
-            i = (k0 + k) % R
-            envs[i].step(acts[i])
+        for k in range(k0, k0 + n):
+            i = k % R
+            envs[i].step(acts[i][(k // R) % K_ACT])
 
     # ---- device-resident throughput: windows of exactly K steps, barrier + sync on both sides, max over ranks per window ----
     run(max(a.warmup, 3))
@@ -317,7 +319,7 @@ def main():
         scrub.fill_(k & 255)                                  # evict the 126 MB L2
         torch.cuda.synchronize()
         ev0.record()
-        envs[k % R].step(acts[k % R])
+        envs[k % R].step(acts[k % R][k % K_ACT])
         ev1.record()
         torch.cuda.synchronize()
         iso.append(ev0.elapsed_time(ev1))
@@ -340,24 +342,29 @@ def main():
 
     # ---- end to end through the NumPy API: page-locked ndarray actions in, ndarrays out, every copy inside step() ----
     h_acts = []
-    for x in acts:
-        t = torch.empty(x.shape, dtype=torch.float32).pin_memory()
-        t.copy_(x)
-        h_acts.append(t.numpy())
+    for xs in acts:
+        row = []
+        for x in xs:
+            t = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+            t.copy_(x)
+            row.append(t.numpy())
+        h_acts.append(row)
     e2e_steps = max(10, min(a.steps, 200))
     for k in range(5):
-        envs[k % R].step(h_acts[k % R])
+        envs[k % R].step(h_acts[k % R][k % K_ACT])
     barrier()
+    n_fin_tot = 0
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         i = k % R
-        obs, rew, term, trunc, info = envs[i].step(h_acts[i])
+        obs, rew, term, trunc, info = envs[i].step(h_acts[i][(k // R) % K_ACT])
+        n_fin_tot += info["final_obs"].shape[0] if "final_obs" in info else 0
     barrier()
     e2e_s = all_max(time.perf_counter() - t0)
     e2e_val = DRONES_PER_GPU * world * e2e_steps / e2e_s
-    n_fin = int(info["final_obs"].shape[0]) if "final_obs" in info else 0
+    n_fin = n_fin_tot / e2e_steps
     h2d = DRONES_PER_GPU * A * 4
-    d2h = DRONES_PER_GPU * OBS_DIM * 4 + E * (4 + 1 + 1 + 1) + n_fin * (D * OBS_DIM * 4 + 8) + 4
+    d2h = int(DRONES_PER_GPU * OBS_DIM * 4 + E * (4 + 1 + 1 + 1) + n_fin * (D * OBS_DIM * 4 + 8) + 4)
     # the link itself, same process, same pinned memory: one 19 MB device -> pinned host copy, repeated
     hbuf = torch.empty((DRONES_PER_GPU, OBS_DIM), dtype=torch.float32).pin_memory()
     dbuf = envs[0]._obs_buf[0]
@@ -372,7 +379,7 @@ def main():
     e2e_gbs = (h2d + d2h) * e2e_steps / (e2e_s) / 1e9 if world == 1 else (h2d + d2h) / (DRONES_PER_GPU / (e2e_val / world)) / 1e9
     e2e = {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
            "ms_per_step": 1e3 * e2e_s / e2e_steps, "d2h_gbs": d2h / (e2e_s / e2e_steps) / 1e9, "pcie_d2h_gbs_measured": pcie_gbs,
-           "pcie_frac": d2h / (e2e_s / e2e_steps) / 1e9 / pcie_gbs, "terminal_obs_aviaries_last_step": n_fin, "numa_binding": numa,
+           "pcie_frac": d2h / (e2e_s / e2e_steps) / 1e9 / pcie_gbs, "terminal_obs_aviaries_per_step": n_fin, "numa_binding": numa,
            "api": "MultiHoverAviary.step(page-locked ndarray) -> ndarrays (qs_step_host: H2D actions, tick, device-side compaction of the "
                   "finished aviaries, D2H obs/reward/flags + their terminal observations; host_copy=False)"}
     del hbuf
@@ -420,9 +427,11 @@ def run_extras(a, envs, acts, gen, dev, world, R, peak_gbs, barrier):
             best = min(best, e0.elapsed_time(e1) / n)
         return best
 
+    K_ACT = len(acts[0])
+
     def run(n):
         for k in range(n):
-            envs[k % R].step(acts[k % R])
+            envs[k % R].step(acts[k % R][(k // R) % K_ACT])
 
     try:   # the same launches replayed from a CUDA graph: no per-step host work
         g = torch.cuda.CUDAGraph()
@@ -482,7 +491,7 @@ def run_extras(a, envs, acts, gen, dev, world, R, peak_gbs, barrier):
                 for k in range(n):
                     i = k % R
                     with torch.cuda.stream(s_even if (i & 1) == 0 else s_odd):
-                        envs[i].step(acts[i])
+                        envs[i].step(acts[i][(k // R) % K_ACT])
                 cur.wait_stream(s_even)
                 cur.wait_stream(s_odd)
 

@@ -48,6 +48,7 @@ struct StepArgs {
     int flags_late_tma;  // experiments (QS_LATE_TMA): 1 = issue the bulk copy only after the state loads have landed
     int prefetch;        // experiments (QS_PREFETCH): 1 = L2 prefetch of the warp's inputs ahead of griddepcontrol.wait
     int early_store;     // experiments (QS_EARLY_STORE): 1 = history written back as soon as it has landed (A = 4)
+    int dbg_slot;        // QS_TIMELINE builds: which timeline buffer this launch stamps
 };
 
 __device__ __forceinline__ float4 ldg4(const float* base, long long idx4) {
@@ -123,8 +124,8 @@ __device__ __forceinline__ void load_drone(const double* planes, long long N, lo
 // normalises the quaternion (the north-star's "quaternion renormalise"; Bullet's own read-back goes through a
 // rotation matrix and renormalises too) and stores the planes (+ the optional float32 position mirror)
 __device__ __forceinline__ void store_drone(const QsState& st, long long N, long long i, qs::Drone& d) {
-    const double inv = rsqrt(d.qx * d.qx + d.qy * d.qy + d.qz * d.qz + d.qw * d.qw);
-    d.qx *= inv; d.qy *= inv; d.qz *= inv; d.qw *= inv;
+    const double inv = rsqrt(qs::quat_norm2(d.qx, d.qy, d.qz, d.qw));
+    d.qx = __dmul_rn(d.qx, inv); d.qy = __dmul_rn(d.qy, inv); d.qz = __dmul_rn(d.qz, inv); d.qw = __dmul_rn(d.qw, inv);
     double* planes = st.planes;
     st256(planes, i, d.px, d.py, d.pz, d.wx);
     st256(planes, N + i, d.qx, d.qy, d.qz, d.qw);

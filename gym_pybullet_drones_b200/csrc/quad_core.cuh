@@ -68,11 +68,34 @@ QS_HD float f32_sqrt(float a) {
 
 QS_HD double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// |q|^2 with a fixed operation order and explicit fused multiply-adds: the compiler's contraction choices depend on the
+// surrounding code, and the renormalised quaternion must be the same bits in every kernel that advances the state
+QS_HD double quat_norm2(double x, double y, double z, double w) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(w, w, __fma_rn(z, z, __fma_rn(y, y, __dmul_rn(x, x))));
+#else
+    return fma(w, w, fma(z, z, fma(y, y, x * x)));
+#endif
+}
+
 // ---- Bullet quaternion helpers ---------------------------------------------------------------
 // getMatrixFromQuaternion (btMatrix3x3::setRotation): row-major R, implicit normalisation by s = 2/|q|^2.
 QS_HD void quat_to_matrix(double x, double y, double z, double w, double R[9]) {
     const double d = x * x + y * y + z * z + w * w;
     const double s = 2.0 / d;
+    const double xs = x * s, ys = y * s, zs = z * s;
+    const double wx = w * xs, wy = w * ys, wz = w * zs;
+    const double xx = x * xs, xy = x * ys, xz = x * zs;
+    const double yy = y * ys, yz = y * zs, zz = z * zs;
+    R[0] = 1.0 - (yy + zz); R[1] = xy - wz;         R[2] = xz + wy;
+    R[3] = xy + wz;         R[4] = 1.0 - (xx + zz); R[5] = yz - wx;
+    R[6] = xz - wy;         R[7] = yz + wx;         R[8] = 1.0 - (xx + yy);
+}
+
+// the same for a quaternion that is unit to rounding (|q|^2 = 1 + e, |e| ~ 1e-15): s = 2/|q|^2 = 2(2 - |q|^2) + O(e^2), no division
+QS_HD void quat_to_matrix_unit(double x, double y, double z, double w, double R[9]) {
+    const double d = x * x + y * y + z * z + w * w;
+    const double s = 2.0 * (2.0 - d);
     const double xs = x * s, ys = y * s, zs = z * s;
     const double wx = w * xs, wy = w * ys, wz = w * zs;
     const double xx = x * xs, xy = x * ys, xz = x * zs;
@@ -198,7 +221,7 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
     // |q|^2 - 1 ~ 1e-16 for the whole tick (_integrateQ is norm preserving), so Bullet's s = 2/|q|^2 is evaluated as
     // 2(2 - |q|^2), exact to (|q|^2-1)^2 -- one DFMA instead of a double-precision division per substep.
     {
-        const double n2 = d.qx * d.qx + d.qy * d.qy + d.qz * d.qz + d.qw * d.qw;
+        const double n2 = quat_norm2(d.qx, d.qy, d.qz, d.qw);
 #if defined(__CUDA_ARCH__)
         const double inv = rsqrt(n2);
 #else
@@ -211,13 +234,17 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
     const double dj0 = dt * P.j_inv[0], dj1 = dt * P.j_inv[1], dj2 = dt * P.j_inv[2];
     const double g21 = P.j[2] - P.j[1], g02 = P.j[0] - P.j[2], g10 = P.j[1] - P.j[0];
     const double gm = dt_m * P.gravity;
+    const double tm2 = 2.0 * (dt_m * thrust), tmg = dt_m * thrust - gm;             // EFF == 0: thrust is constant over the tick
     for (int s = 0; s < substeps; ++s) {
         q0x = d.qx; q0y = d.qy; q0z = d.qz; q0w = d.qw;
         const double x = d.qx, y = d.qy, z = d.qz, w = d.qw;
         // Bullet's s = 2/|q|^2 (:836): |q|^2 = 1 to 1e-16 for the whole tick (unit on entry, _integrateQ is norm preserving)
-        const double xs = x + x, ys = y + y, zs = z + z;
-        // third column and third row of R
-        const double r02 = x * zs + w * ys, r12 = y * zs - w * xs, r22 = 1.0 - (x * xs + y * ys);
+        double r02 = 0.0, r12 = 0.0, r22 = 0.0, xs = 0.0, ys = 0.0, zs = 0.0;
+        if (EFF != 0) {
+            xs = x + x; ys = y + y; zs = z + z;
+            // third column and third row of R
+            r02 = x * zs + w * ys; r12 = y * zs - w * xs; r22 = 1.0 - (x * xs + y * ys);
+        }
         if (EFF & QS_EFFECT_GND) {                                                   // :715-750 on the substep-start state
             const double r20 = x * zs - w * ys, r21 = y * zs + w * xs;
             const double sarg = -2.0 * (x * z - w * y);
@@ -239,11 +266,11 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
             ty = (P.sy[0] * f0 + P.sy[1] * f1 + P.sy[2] * f2 + P.sy[3] * f3) * P.ky;
         }
         if (EFF == 0) {
-            // v += dt (R[:,2] thrust - [0,0,GRAVITY]) / M   (:840-841,:858,:860), one FMA per axis
-            const double tm = dt_m * thrust;
-            d.vx = d.vx + r02 * tm;
-            d.vy = d.vy + r12 * tm;
-            d.vz = d.vz + (r22 * tm - gm);
+            // v += dt (R[:,2] thrust - [0,0,GRAVITY]) / M   (:840-841,:858,:860) with R[:,2] = (2(xz+wy), 2(yz-wx), 1-2(xx+yy)):
+            // the factor 2 rides on the per-tick constant, the column itself is never formed (10 instead of 14 operations)
+            d.vx = d.vx + (x * z + w * y) * tm2;
+            d.vy = d.vy + (y * z - w * x) * tm2;
+            d.vz = (d.vz + tmg) - (x * x + y * y) * tm2;
         } else {
             double fx = r02 * thrust, fy = r12 * thrust, fz = r22 * thrust - P.gravity;  // :840-841
             if (EFF & QS_EFFECT_DRAG) {                                                  // world force = -DRAG_COEFF*sum (.) vel
@@ -273,7 +300,7 @@ QS_HD void dyn_tick(const QsParams& P, Drone& d, const double rpm[4], const doub
         integrate_q(d, dt);                                                          // :863
         between(s);
     }
-    quat_to_matrix(q0x, q0y, q0z, q0w, R_last);                                      // R used by :873 (ang_v = R_old w_new)
+    quat_to_matrix_unit(q0x, q0y, q0z, q0w, R_last);                                 // R used by :873 (ang_v = R_old w_new)
 }
 
 template <bool RPY_F32>

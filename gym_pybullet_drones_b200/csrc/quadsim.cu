@@ -99,6 +99,45 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ Rese
     }
 }
 
+// learner side of the fused observation gather: wait until every rank's flag carries the sequence number
+__global__ void wait_flags_kernel(const unsigned* flags, unsigned seq, int world, unsigned* err) {
+    if ((int)threadIdx.x < world) {
+        const long long t0 = clock64();
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (clock64() - t0 > 4000000000LL) { if (err) atomicExch(err, 1u); break; }
+        } while ((int)(v - seq) < 0);
+    }
+}
+
+// one Logger entry per logged drone (utils/Logger.py:83-119), appended to the device ring
+__global__ void log_append_kernel(QsParams P, QsState st, const float* __restrict__ obs, int obs_dim, const float* __restrict__ controls,
+                                  QsLogRing rg, long long N, int D) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long head = *rg.head;
+    if (j < rg.n_drones) {
+        const long long i = rg.first_drone + j;
+        qs::Drone d;
+        load_drone(st.planes, N, i, d);
+        double roll, pitch, yaw;
+        qs::quat_to_euler<false>(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
+        const float* row = obs + i * obs_dim;
+        const int av = obs_dim == 20 ? 13 : 9;                                  // ang_v in a state vector / in a KIN row
+        double* o = rg.ring + ((head % rg.capacity) * rg.n_drones + j) * 32;
+        o[0] = d.px; o[1] = d.py; o[2] = d.pz; o[3] = d.vx; o[4] = d.vy; o[5] = d.vz;          // Logger.py:117
+        o[6] = roll; o[7] = pitch; o[8] = yaw;
+        o[9] = row[av]; o[10] = row[av + 1]; o[11] = row[av + 2];
+        double rpm[4] = {0, 0, 0, 0};
+        if (st.last_rpm) load_rpm(st.last_rpm, i, rpm);
+        o[12] = rpm[0]; o[13] = rpm[1]; o[14] = rpm[2]; o[15] = rpm[3];
+        for (int k = 0; k < 12; ++k) o[16 + k] = controls ? (double)controls[12 * j + k] : 0.0;
+        o[28] = (double)st.step_counter[i / D] * P.dt;                          // simulation time after the tick
+        o[29] = o[30] = o[31] = 0.0;
+    }
+}
+__global__ void log_advance_kernel(long long* head) { *head += 1; }      // after every CTA of the append has read it (stream order)
+
 __global__ void reset_heads_kernel(QsState st, int rows, int rpyf, float* __restrict__ out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
@@ -277,6 +316,11 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
         if (io->obs && io->act_buffer_size > 0 && !state20 && span <= kStageLimit) a.stage_rows = (aligned && A == 4) ? 1 : 2;
     }
     const bool fast_off = getenv("QS_FAST") && atoi(getenv("QS_FAST")) == 0;      // A/B and bit-identity tests: force the general kernel
+    if (io->obs_gather) {
+        if (fast_off || !step_fast_eligible(a)) return fail(QS_ERR_UNSUPPORTED, "qs_step: obs_gather needs a configuration of step_fast.cu (RPM / ONE_D_RPM, no effects, D | 32)");
+        if (!aligned16(io->obs_gather)) return fail(QS_ERR_ALIGN, "qs_step: obs_gather must be 16-byte aligned");
+        if (io->gather_flag && !io->gather_counter) return fail(QS_ERR_NULL, "qs_step: gather_flag needs gather_counter");
+    }
     const cudaError_t e = (!fast_off && step_fast_eligible(a)) ? launch_step_fast(a, (cudaStream_t)stream)
                                                                : launch_step_general(a, state20, pid_act, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_step launch");
@@ -405,6 +449,31 @@ int qs_pid_control(const QsParams* p, double* pid_state, double control_timestep
     pid_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_pid_control launch");
+}
+
+int qs_wait_flags(const unsigned* flags, unsigned seq, int world, unsigned* err_flag, void* stream) {
+    if (!flags) return fail(QS_ERR_NULL, "qs_wait_flags: NULL flags");
+    if (world <= 0 || world > QS_MAX_PEERS) return fail(QS_ERR_SIZE, "qs_wait_flags: world must be in [1, QS_MAX_PEERS]");
+    wait_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, seq, world, err_flag);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "qs_wait_flags launch");
+}
+
+int qs_sizeof_log_ring(void) { return (int)sizeof(QsLogRing); }
+
+int qs_log_append(const QsParams* p, const QsState* st, const float* obs, int obs_dim, const float* controls,
+                  const QsLogRing* ring, int n_envs, int drones_per_env, void* stream) {
+    if (!p || !ring || !ring->ring || !ring->head || !obs) return fail(QS_ERR_NULL, "qs_log_append: NULL argument");
+    if (int rc = check_state(st, 0)) return rc;
+    if (n_envs <= 0 || drones_per_env <= 0 || ring->capacity <= 0 || ring->n_drones <= 0 || ring->first_drone < 0 ||
+        (long long)ring->first_drone + ring->n_drones > (long long)n_envs * drones_per_env)
+        return fail(QS_ERR_SIZE, "qs_log_append: bad ring geometry");
+    if (obs_dim < 12) return fail(QS_ERR_SIZE, "qs_log_append: obs_dim < 12");
+    const int blocks = (ring->n_drones + 127) / 128;
+    log_append_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(*p, *st, obs, obs_dim, controls, *ring, (long long)n_envs * drones_per_env, drones_per_env);
+    log_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ring->head);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "qs_log_append launch");
 }
 
 int qs_reset_heads(const QsState* st, int rows, unsigned flags, float* out, void* stream) {

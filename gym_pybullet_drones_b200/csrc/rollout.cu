@@ -32,8 +32,8 @@ __device__ __forceinline__ float u32_to_pm1(unsigned u) { return (float)(u >> 8)
 // what store_drone + load_drone do to the state between two ticks: the quaternion is renormalised, nothing is rounded
 // (the planes are float64), so T fused ticks equal T calls of qs_step bit for bit
 __device__ __forceinline__ void round_to_planes(qs::Drone& d) {
-    const double inv = rsqrt(d.qx * d.qx + d.qy * d.qy + d.qz * d.qz + d.qw * d.qw);
-    d.qx *= inv; d.qy *= inv; d.qz *= inv; d.qw *= inv;
+    const double inv = rsqrt(qs::quat_norm2(d.qx, d.qy, d.qz, d.qw));
+    d.qx = __dmul_rn(d.qx, inv); d.qy = __dmul_rn(d.qy, inv); d.qz = __dmul_rn(d.qz, inv); d.qw = __dmul_rn(d.qw, inv);
 }
 
 template <int EFF, bool PIDACT>

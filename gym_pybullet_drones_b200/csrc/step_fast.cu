@@ -18,8 +18,9 @@
 
 #ifdef QS_TIMELINE
 // debug build only (tools/timeline.py): per-warp phase timestamps (%globaltimer, ns) of the last launch
-__device__ unsigned long long g_timeline[8192 * 16];
-#define QS_STAMP(k) do { if (lane == 0 && wg < 8192) g_timeline[wg * 16 + (k)] = globaltimer_ns(); } while (0)
+__device__ unsigned long long g_timeline[4][8192 * 16];
+static int g_dbg_slot = 0;
+#define QS_STAMP(k) do { if (lane == 0 && wg < 8192) g_timeline[a.dbg_slot & 3][wg * 16 + (k)] = globaltimer_ns(); } while (0)
 #else
 #define QS_STAMP(k) do { } while (0)
 #endif
@@ -86,8 +87,8 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
             pf(a.st.planes + 4 * w0, nb); pf(a.st.planes + 4 * (N + w0), nb); pf(a.st.planes + 4 * (2 * N + w0), nb);
             if (((rows * 8) & 15) == 0) pf(a.st.planes + 12 * N + w0, (unsigned)rows * 8u);
             if (((rows * A * 4) & 15) == 0) pf(a.io.action + w0 * A, (unsigned)(rows * A * 4));
-            pf(span_src, span_bytes);
-        }
+            if (a.prefetch > 1) pf(span_src, span_bytes);      // (the history follows the state loads through the bulk copy: prefetching
+        }                                                      //  it too delays the state of an isolated launch, measured)
     }
     __syncwarp();
     // read-only tables (never written by a kernel): safe ahead of the dependency wait
@@ -156,6 +157,8 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
 
     // ---- task terms, reduced over the D drones of the aviary in index order (MultiHoverAviary.py:75-130) ----------------------
     bool env_done = false;
+    float g_rew = -1.0f;
+    bool g_term = false, g_trunc = false;
     if (TASK) {
         const qs::TaskTerms tt = qs::hover_terms(P, d, o, tpx, tpy, tpz);
         double rew = 0.0, dist = 0.0;
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
         const bool term = dist < P.term_dist;                                     // HoverAviary.py:91
         const bool trunc = (oobs & gmask) != 0u || sc >= a.sc_limit;              // HoverAviary.py:113 (sc/PYB_FREQ > EPISODE_LEN_SEC)
         env_done = term || trunc;
+        g_rew = (float)rew; g_term = term; g_trunc = trunc;
         if (live && dslot == 0) {
             a.io.reward[e] = (float)rew;
             a.io.terminated[e] = term ? 1 : 0;
@@ -211,6 +215,43 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
     // ---- observation rows --------------------------------------------------------------------------------------------------------
     if (!issued && lane == 0) tma_bulk_g2s(xs, span_src, span_bytes, bar);
     const unsigned fin_rows = want_fin ? __ballot_sync(0xffffffffu, reset_me && live) : 0u;
+    // Fused observation gather: the finished rows go a second time, straight from shared memory, to the learner's tensor
+    // (peer memory over NVLink), the per-aviary outputs with them; the last warp of the grid raises the learner's flag.
+    auto gather = [&](const void* rows_smem) {
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(a.io.obs_gather + w0 * od), "r"(smem_u32(rows_smem)), "r"(span_bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (live && dslot == 0) {
+            if (a.io.reward_gather) a.io.reward_gather[e] = g_rew;
+            if (a.io.terminated_gather) a.io.terminated_gather[e] = g_term ? 1 : 0;
+            if (a.io.truncated_gather) a.io.truncated_gather[e] = g_trunc ? 1 : 0;
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // rows written (not only read) before the flag
+        __syncwarp();
+        if (a.io.gather_flag) {
+            __threadfence_system();
+            if (lane == 0) {
+                const unsigned nwarps = (unsigned)((N + 31) / 32);
+                if (atomicAdd(a.io.gather_counter, 1u) == nwarps - 1u) {
+                    *a.io.gather_counter = 0u;
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.io.gather_flag), "r"(a.io.gather_seq) : "memory");
+                }
+            }
+        }
+    };
+    auto patch_rows_a4 = [&]() {            // new head -> slots [A, A+12) of my row, new action -> the A slots after it (in place)
+        if (live) {
+            float* row = xs + (size_t)lane * od;
+            float4* r4 = reinterpret_cast<float4*>(row + 4);
+            r4[0] = make_float4(h[0], h[1], h[2], h[3]); r4[1] = make_float4(h[4], h[5], h[6], h[7]); r4[2] = make_float4(h[8], h[9], h[10], h[11]);
+            *reinterpret_cast<float4*>(row + od) = make_float4(act[0], act[1], act[2], act[3]);
+        }
+        __syncwarp();
+    };
     if (A == 4 && a.early_store) {
         if (!stored) { mbar_wait(bar, 0); store_span(); }
         if (want_fin) {                                                            // terminal observations: head from fin_s, history from the span
@@ -236,18 +277,13 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
             row[(od >> 2) - 1] = make_float4(act[0], act[1], act[2], act[3]);
         }
         QS_STAMP(8);
+        if (a.io.obs_gather) { patch_rows_a4(); gather(shifted); }      // (the early bulk store has completed: shared memory is free)
         return;
     }
     mbar_wait(bar, 0);
     QS_STAMP(7);
     if (A == 4) {
-        if (live) {
-            float* row = xs + (size_t)lane * od;
-            float4* r4 = reinterpret_cast<float4*>(row + 4);
-            r4[0] = make_float4(h[0], h[1], h[2], h[3]); r4[1] = make_float4(h[4], h[5], h[6], h[7]); r4[2] = make_float4(h[8], h[9], h[10], h[11]);
-            *reinterpret_cast<float4*>(row + od) = make_float4(act[0], act[1], act[2], act[3]);
-        }
-        __syncwarp();
+        patch_rows_a4();
         if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         store_span();
         if (want_fin) {                                                            // terminal observations: head from fin_s, history from the span
@@ -291,6 +327,7 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
         }
     }
     QS_STAMP(8);
+    if (a.io.obs_gather) { gather(A == 4 ? (const void*)shifted : (const void*)ys); return; }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the bulk store's reads
     QS_STAMP(9);
 }
@@ -347,7 +384,13 @@ bool step_fast_eligible(const StepArgs& a) {
     return true;
 }
 
-cudaError_t launch_step_fast(const StepArgs& a, cudaStream_t s) {
+cudaError_t launch_step_fast(const StepArgs& a_in, cudaStream_t s) {
+#ifdef QS_TIMELINE
+    StepArgs a = a_in;
+    a.dbg_slot = g_dbg_slot;
+#else
+    const StepArgs& a = a_in;
+#endif
     static const int warps = getenv("QS_FAST_WARPS") ? atoi(getenv("QS_FAST_WARPS")) : 1;      // measured default
     if (a.A == 4) {
         if (warps == 4) return launch_modes<4, 4>(a, s);
@@ -362,7 +405,8 @@ cudaError_t launch_step_fast(const StepArgs& a, cudaStream_t s) {
 }  // namespace qsi
 
 #ifdef QS_TIMELINE
-extern "C" int qs_debug_timeline(unsigned long long* host_out, int n_words) {
-    return (int)cudaMemcpyFromSymbol(host_out, g_timeline, (size_t)n_words * 8);
+extern "C" int qs_debug_timeline(unsigned long long* host_out, int n_words, int slot) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_timeline, (size_t)n_words * 8, (size_t)(slot & 3) * 8192 * 16 * 8);
 }
+extern "C" void qs_debug_set_slot(int slot) { g_dbg_slot = slot; }
 #endif

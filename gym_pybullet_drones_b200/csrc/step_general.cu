@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
         unsigned char mode = pending ? (unsigned char)(1 | ((a.flags & QS_FLAG_AUTORESET_CLEARS_HISTORY) ? 4 : 0)) : (unsigned char)0;
         if (RAW) {
             // _getDroneStateVector (BaseAviary.py:541-561); quaternion reported normalised
-            const double inv = rsqrt(d.qx * d.qx + d.qy * d.qy + d.qz * d.qz + d.qw * d.qw);
+            const double inv = rsqrt(qs::quat_norm2(d.qx, d.qy, d.qz, d.qw));
             h[0] = (float)d.px; h[1] = (float)d.py; h[2] = (float)d.pz;
             h[3] = (float)(d.qx * inv); h[4] = (float)(d.qy * inv); h[5] = (float)(d.qz * inv); h[6] = (float)(d.qw * inv);
             h[7] = (float)o.roll; h[8] = (float)o.pitch; h[9] = (float)o.yaw;

@@ -166,6 +166,8 @@ class BaseAviary(Env):
                 self._flags &= ~(N.FLAG_AUTORESET_SAME_STEP | N.FLAG_AUTORESET_NEXT_STEP)
         self.metadata = dict(self.metadata, autoreset_mode=self.autoreset_mode)
         self._host_copy = host_copy
+        self._log = None                     # (QsLogRing, controls tensor) while a utils.Logger is attached
+        self._gather = None                  # sharding.ObsGather: the tick also writes its rows into the learner's tensor
         #### Initial poses (BaseAviary.py:194-207); [D,3] shared by all aviaries or [E,D,3] per aviary ####
         self._tables_per_env = False
         if initial_xyzs is None:
@@ -512,7 +514,16 @@ class BaseAviary(Env):
                                    self._E, self._D, 1, self._effects, fl, stream)
                 N.check(rc, "qs_step(split)")
         self._cur = 1 - cur
+        if self._log is not None:
+            self._log_append()
         return self._obs_buf[self._cur]
+
+    def _log_append(self):
+        """One entry per logged drone into the attached device ring (utils.Logger.attach, qs_log_append)."""
+        ring, controls = self._log
+        N.check(self._lib.qs_log_append(C.byref(self._P), C.byref(self._st), self._obs_ptr[self._cur], self._obs_dim,
+                                        controls.data_ptr() if controls is not None else None, C.byref(ring), self._E, self._D,
+                                        torch.cuda.current_stream(self.device).cuda_stream), "qs_log_append")
 
     def _downwash_stage(self, stream):
         """Pairwise downwash force of the current positions into `_dw_fz` (BaseAviary.py:785-811), once per substep."""
@@ -548,11 +559,15 @@ class BaseAviary(Env):
             io.action = a.data_ptr()
             io.obs_prev = self._obs_ptr[cur]
             io.obs = self._obs_ptr[1 - cur]
+            if self._gather is not None:
+                self._gather.arm(io)
             stream = self._raw_stream(self._dev_index) if self._raw_stream else torch.cuda.current_stream().cuda_stream
             rc = self._qs_step_call(self._call_ptr, stream)
             if rc:
                 N.check(rc, "qs_step")
             self._cur = cur = 1 - cur
+            if self._log is not None:
+                self._log_append()
             if self._final_view is None:
                 return self._obs_view[cur], self._reward, self._terminated, self._truncated, {}
             return (self._obs_view[cur], self._reward, self._terminated, self._truncated,
@@ -620,6 +635,8 @@ class BaseAviary(Env):
         if rc:
             N.check(rc, "qs_step_host")
         self._cur = 1 - cur
+        if self._log is not None:
+            self._log_append()
         o, rew, term, trunc = self._h_np[k]
         info = {}
         if self._final_obs is not None:

@@ -4,7 +4,10 @@ Same constructor, `log(drone, timestamp, state, control)`, `save()` and array la
 [D, T], `states` [D, 16, T] in the reference's re-ordered layout (pos3, vel3, rpy3, ang_v3, rpm4; Logger.py:117) and
 `controls` [D, 12, T], saved with `np.savez` under the same keys -- so existing analysis scripts keep working.  Added
 for the vectorised envs: `log_all(timestamp, states[D, 20], controls[D, 12])` logs every drone of an aviary with one
-call.  Plotting (`Logger.plot`, Logger.py:205-379) needs matplotlib, which is optional.
+call, and `attach(env, aviary)`: the env then appends one entry per drone of that aviary after EVERY control tick to a
+ring in device memory (qs_log_append: 16 states + 12 controls + time, float64), with no host transfer until `flush()` /
+`save()` -- logging a vectorised env no longer costs a D2H copy per tick.  Plotting (`Logger.plot`, Logger.py:205-379)
+needs matplotlib, which is optional.
 """
 import os
 from datetime import datetime
@@ -59,12 +62,68 @@ class Logger(object):
             self.controls[:, :, c] = np.asarray(controls, dtype=np.float64).reshape(self.NUM_DRONES, 12)
         self.counters[:] = c + 1
 
+    # ---- device-side ring --------------------------------------------------------------------------
+    def attach(self, env, aviary: int = 0, capacity: int = None):
+        """Starts logging every control tick of `env`'s aviary `aviary` (its NUM_DRONES drones) on the device.
+        `capacity` = ticks the ring holds between two flush() calls (default: duration_sec * logging_freq_hz, else 4096)."""
+        import ctypes as C
+        import torch
+        from .. import _native as N
+        if env.NUM_DRONES != self.NUM_DRONES:
+            raise ValueError("Logger(num_drones=%d) attached to an env with %d drones per aviary" % (self.NUM_DRONES, env.NUM_DRONES))
+        if not 0 <= aviary < env.num_envs:
+            raise ValueError("aviary index out of range")
+        cap = int(capacity or (self.timestamps.shape[1] if self.PREALLOCATED_ARRAYS else 4096))
+        self._ring = torch.zeros((cap, self.NUM_DRONES, 32), dtype=torch.float64, device=env.device)
+        self._head = torch.zeros((1,), dtype=torch.int64, device=env.device)
+        self._ctrl_dev = torch.zeros((self.NUM_DRONES, 12), dtype=torch.float32, device=env.device)
+        rg = N.QsLogRing()
+        rg.ring, rg.head, rg.capacity = self._ring.data_ptr(), self._head.data_ptr(), cap
+        rg.first_drone, rg.n_drones = aviary * env.NUM_DRONES, self.NUM_DRONES
+        self._rg, self._env, self._flushed = rg, env, 0
+        env._log = (rg, self._ctrl_dev)
+        return self
+
+    def set_controls(self, controls):
+        """Control targets [D, 12] logged with the following ticks (Logger.py:59-72); ndarray or CUDA tensor."""
+        import torch
+        c = controls if isinstance(controls, torch.Tensor) else torch.as_tensor(np.asarray(controls, dtype=np.float32))
+        self._ctrl_dev.copy_(c.to(dtype=torch.float32).reshape(self.NUM_DRONES, 12), non_blocking=True)
+
+    def detach(self):
+        self.flush()
+        self._env._log = None
+        self._env = None
+
+    def flush(self):
+        """Copies the entries appended since the last flush from the device ring into the host arrays (one D2H)."""
+        if getattr(self, "_env", None) is None:
+            return 0
+        head = int(self._head.item())
+        cap = self._rg.capacity
+        n_new = head - self._flushed
+        if n_new <= 0:
+            return 0
+        if n_new > cap:
+            raise RuntimeError("Logger ring overflow: %d ticks since the last flush(), capacity %d" % (n_new, cap))
+        idx = np.arange(self._flushed, head) % cap
+        rows = self._ring.cpu().numpy()[idx]                  # [n_new, D, 32]
+        c = int(self.counters.max())
+        self._grow(c + n_new)
+        self.timestamps[:, c:c + n_new] = rows[:, :, 28].T
+        self.states[:, :, c:c + n_new] = rows[:, :, 0:16].transpose(1, 2, 0)
+        self.controls[:, :, c:c + n_new] = rows[:, :, 16:28].transpose(1, 2, 0)
+        self.counters[:] = c + n_new
+        self._flushed = head
+        return n_new
+
     def _trimmed(self):
         n = int(self.counters.max()) if not self.PREALLOCATED_ARRAYS else self.timestamps.shape[1]
         return self.timestamps[:, :n], self.states[:, :, :n], self.controls[:, :, :n]
 
     def save(self):
         """np.savez(timestamps=, states=, controls=) like the reference (Logger.py:123-127); returns the path."""
+        self.flush()
         ts, st, ct = self._trimmed()
         path = os.path.join(self.OUTPUT_FOLDER, "save-flight-" + datetime.now().strftime("%m.%d.%Y_%H.%M.%S") + ".npy")
         with open(path, 'wb') as out_file:

@@ -18,6 +18,7 @@
  *   qs_downwash_rows / qs_dw_publish <- the same loop for one formation sharded over GPUs (rows = local drones)
  *   qs_adjacency     <- BaseAviary._getAdjacencyMatrix (envs/BaseAviary.py:658-675)
  *   qs_reset         <- BaseAviary.reset/_housekeeping (envs/BaseAviary.py:220-255,451-505)
+ *   qs_log_append    <- Logger.log (utils/Logger.py:83-119): one entry per logged drone and tick, kept on the device
  *
  * Conventions
  *   - plain C, no CUDA/torch types: device buffers are raw pointers owned by the caller; the
@@ -154,7 +155,24 @@ typedef struct QsStepIO {
     int act_buffer_size;        /* B = ctrl_freq//2 (BaseRLAviary.py:66); 0 for RAW_RPM */
     int tick_substeps;          /* physics steps the step counter advances by in the epilogue; 0 = `substeps`
                                    (only the split-substep protocol passes PYB_STEPS_PER_CTRL here) */
+    /* Fused observation gather ("optional all-gather of observations where the learner wants a single tensor"):
+     * a second destination for this tick's rows, normally the LEARNER GPU's [E_total][D][obs_dim] tensor at this rank's
+     * row offset, mapped into this process by CUDA IPC / peer access.  The kernel's bulk store writes the finished rows
+     * straight over NVLink (no separate collective), per-aviary reward/flags likewise, and the last warp to finish raises
+     * *gather_flag to gather_seq with release semantics at system scope (the learner waits with qs_wait_flags).  All NULL =
+     * off.  Supported by the RL configurations of step_fast.cu (QS_ERR_UNSUPPORTED otherwise). */
+    float* obs_gather;                  /* [N][obs_dim] rows of THIS rank inside the gathered tensor */
+    float* reward_gather;               /* [E] nullable */
+    unsigned char* terminated_gather;   /* [E] nullable */
+    unsigned char* truncated_gather;    /* [E] nullable */
+    unsigned* gather_flag;              /* one word on the learner, nullable */
+    unsigned* gather_counter;           /* one zeroed device word owned by the caller (arrival count); required with gather_flag */
+    unsigned gather_seq;
+    unsigned pad_;
 } QsStepIO;
+
+/* Spins (bounded, ~2 s, then *err_flag = 1) until flags[r] - seq >= 0 for every r < world: the learner side of obs_gather. */
+int qs_wait_flags(const unsigned* flags, unsigned seq, int world, unsigned* err_flag, void* stream);
 
 /* Multi-tick rollout: T control ticks in ONE launch (the caller is SB3's collect_rollouts,
  * examples/learn.py:93).  Exactly T calls of qs_step with SAME_STEP (or no) autoreset, but the drone state stays in
@@ -296,6 +314,22 @@ int qs_adjacency(const QsState* st, int n_envs, int drones_per_env, double radiu
  * reset drone: (float)INIT_XYZS, rpy of the initial quaternion (float32 atan2f/asinf iff flags has QS_FLAG_RPY_F32), zeros --
  * exactly what the tick writes for an aviary it resets.  Point QsState.reset_head at it afterwards. */
 int qs_reset_heads(const QsState* st, int rows, unsigned flags, float* out, void* stream);
+
+/* Device-side trajectory ring in the reference Logger's layout (utils/Logger.py:83-127).  One call appends ONE entry for
+ * each of the drones [first_drone, first_drone + n_drones): the 16 logged states in Logger.py:117 order (pos3, vel3, rpy3,
+ * ang_v3, rpm4), the 12 control targets, the simulation time of the entry and 3 pad doubles -- 32 float64 per drone and
+ * entry, ring[(head % capacity)][drone][32]; the kernel then advances *head.  pos/vel/rpm come from the float64 state
+ * (planes, last_rpm), rpy is re-evaluated from the quaternion in float64, ang_v is taken from the observation rows
+ * (float32: obs_dim = 20 state vectors or KIN rows).  controls: [n_drones][12] float32 device array or NULL (zeros).
+ * Nothing crosses PCIe until the caller copies the ring (Logger.save). */
+typedef struct QsLogRing {
+    double* ring;            /* [capacity][n_drones][32] */
+    long long* head;         /* device counter: entries appended so far */
+    int capacity, first_drone, n_drones, pad_;
+} QsLogRing;
+int qs_sizeof_log_ring(void);
+int qs_log_append(const QsParams* p, const QsState* st, const float* obs, int obs_dim, const float* controls,
+                  const QsLogRing* ring, int n_envs, int drones_per_env, void* stream);
 
 /* Reset envs to their initial pose.  mask: [E] bytes, nullable = all envs.  Zeroes velocities, body rates,
  * last_rpm, step counter; with reset_pid != 0 also the PID state (the reference never does).

@@ -16,7 +16,7 @@ void load(const double* planes, long long N, long long i, qs::Drone& d) {
     d.wx = p0[3]; d.wy = p2[3]; d.wz = planes[12 * N + i];
 }
 void store(double* planes, long long N, long long i, qs::Drone& d) {
-    const double inv = 1.0 / std::sqrt(d.qx * d.qx + d.qy * d.qy + d.qz * d.qz + d.qw * d.qw);
+    const double inv = 1.0 / std::sqrt(qs::quat_norm2(d.qx, d.qy, d.qz, d.qw));
     d.qx *= inv; d.qy *= inv; d.qz *= inv; d.qw *= inv;
     double* p0 = planes + 4 * i; double* p1 = planes + 4 * (N + i); double* p2 = planes + 4 * (2 * N + i);
     p0[0] = d.px; p0[1] = d.py; p0[2] = d.pz; p0[3] = d.wx;

@@ -255,13 +255,13 @@ def test_user_subclass_hooks_are_honoured():
     n_done = 0
     for t in range(60):
         a = torch.rand((E, 1, 4), device="cuda", generator=g)
-        z_before = venv.pos[:, 0, 2].clone()
         obs, r, te, tr, info = venv.step(a)
-        assert r.shape == (E,) and te.dtype == torch.bool and not bool(tr.any())
-        done = info["_final_obs"]
-        assert torch.equal(done, te)
+        z_after = info["final_obs"][:, 0, 2]
+        assert r.shape == (E,) and te.dtype == torch.bool and torch.equal(te, z_after > 0.15)
+        done = info["_final_obs"]                 # _computeTruncated is not overridden: the kernel's Hover truncation still applies
+        assert torch.equal(done, te | tr)
         # finished aviaries were reset by the host side: back at the initial height, terminal observation kept
-        assert torch.all(venv.pos[done][:, 0, 2] == venv.INIT_XYZS[0, 2]) and torch.all(info["final_obs"][done][:, 0, 2] > 0.15)
+        assert torch.all(venv.pos[done][:, 0, 2] == venv.INIT_XYZS[0, 2])
         assert torch.all(venv.step_counter[done] == 0)
         n_done += int(done.sum())
     assert n_done > 0
@@ -277,3 +277,71 @@ def test_user_subclass_hooks_are_honoured():
         o, *_ = c.step(frac)
         o2, *_ = cref.step(np.repeat(frac * cref.MAX_RPM, 4, axis=-1))
         assert np.array_equal(o, o2)
+
+
+def test_device_logger_ring_matches_reference_logger_layout(golden, tmp_path):
+    """a utils.Logger attached to a CtrlAviary logs every tick on the device (qs_log_append); after the
+    pid.py circle (teacher-forced from the golden states, like test_pid_circle_workload) its .npy equals what the
+    reference's Logger.log(drone, t, state, control) produces when fed the golden state vectors (Logger.py:83-127)."""
+    from gym_pybullet_drones_b200.control import DSLPIDControl
+    from gym_pybullet_drones_b200.envs import CtrlAviary
+    from gym_pybullet_drones_b200.utils import Logger
+    from gym_pybullet_drones_b200.utils.enums import DroneModel, Physics
+    g = golden("pid_circle_cf2x")
+    T = 60
+    env = CtrlAviary(num_drones=3, initial_xyzs=g["INIT_XYZS"], initial_rpys=g["INIT_RPYS"], physics=Physics.DYN, pyb_freq=240, ctrl_freq=48)
+    lg = Logger(logging_freq_hz=48, output_folder=str(tmp_path), num_drones=3).attach(env, capacity=40)
+    host = Logger(logging_freq_hz=48, output_folder=str(tmp_path / "h"), num_drones=3)        # host-side log() of the GOLDEN states
+    env.reset()
+    for t in range(T):
+        if t > 0:
+            st = g["obs"][t - 1]
+            env.set_state(pos=st[:, 0:3], quat=st[:, 3:7], vel=st[:, 10:13], rpy_rates=g["rpy_rates"][t - 1])
+        ctrl = np.hstack([g["target"][t], g["INIT_RPYS"], np.zeros((3, 6))])
+        lg.set_controls(ctrl)
+        env.step(g["action"][t - 1] if t > 0 else np.zeros((3, 4)))
+        for j in range(3):
+            host.log(drone=j, timestamp=(t + 1) * 5 / 240, state=g["obs"][t][j], control=ctrl[j])
+        if t == 25:
+            assert lg.flush() == 26                      # ring of 40 entries: flushed before it wraps (the next 34 wrap around)
+    d = np.load(lg.save())
+    ts, st, ct = host._trimmed()
+    assert d["timestamps"].shape == (3, T) and d["states"].shape == (3, 16, T) and d["controls"].shape == (3, 12, T)
+    assert np.allclose(d["timestamps"], ts, atol=1e-12) and np.array_equal(d["controls"], ct.astype(np.float32).astype(np.float64))
+    err = np.abs(d["states"] - st) / np.maximum(np.abs(st), 1.0)
+    # the RPMs enter CtrlAviary as float32 (6e-8): 2.5e-8 m/s on the velocity of one tick; ang_v is read from the float32 observation
+    assert err[:, 0:9].max() < 1e-6 and err[:, 9:12].max() < 2e-6 and err[:, 12:16].max() < 1e-7, err.max(axis=(0, 2))
+
+
+@pytest.mark.parametrize("act,world", [("RPM", 3), ("ONE_D_RPM", 2)])
+def test_fused_observation_gather_in_process(act, world):
+    """sharding.ObsGather: every shard's step kernel writes its finished rows, rewards and flags straight into the learner's
+    [E_total, D, obs_dim] tensor and raises its flag; after wait() the learner's tensors equal what ONE env over all aviaries
+    returns, bit for bit (shards on one device here, each on its own stream; tools/gather_multi_gpu.py runs it across GPUs)."""
+    from gym_pybullet_drones_b200.envs import MultiHoverAviary
+    from gym_pybullet_drones_b200.sharding import ObsGather, shard_envs
+    from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
+    E, D, T = 96 * world + 32, 2, 30
+    A = 4 if act == "RPM" else 1
+    kw = dict(num_drones=D, physics=Physics.DYN, act=ActionType[act], autoreset="same_step")
+    ref = MultiHoverAviary(num_envs=E, **kw)
+    shards = [shard_envs(E, r, world) for r in range(world)]
+    envs = [MultiHoverAviary(num_envs=s.count, **kw) for s in shards]
+    gathers = [ObsGather(e, s, learner=0, local=True) for e, s in zip(envs, shards)]
+    ObsGather.connect_local(gathers)
+    streams = [torch.cuda.Stream() for _ in envs]
+    ref.reset()
+    for e in envs:
+        e.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(T):
+        a = torch.rand((E, D, A), device="cuda", generator=g) * 2 - 1
+        o, r, te, tr, _ = ref.step(a)
+        torch.cuda.synchronize()
+        for e, s, st in zip(envs, shards, streams):
+            with torch.cuda.stream(st):
+                e.step(a[s.start:s.stop].contiguous())
+        go, gr, gte, gtr = gathers[0].wait()
+        torch.cuda.synchronize()
+        assert not gathers[0].timed_out()
+        assert torch.equal(go, o) and torch.equal(gr, r) and torch.equal(gte, te) and torch.equal(gtr, tr), t

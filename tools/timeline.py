@@ -57,21 +57,34 @@ def main():
     for k in range(64):
         envs[k % R].step(acts[k % R])
     torch.cuda.synchronize()
+    L = N.lib()
+    nw = min(n // 32, 8192)
+
+    def fetch(slot):
+        b = np.zeros(nw * 16, np.uint64)
+        rc = L.qs_debug_timeline(b.ctypes.data_as(C.c_void_p), C.c_int(nw * 16), C.c_int(slot))
+        assert rc == 0, rc
+        return b.reshape(nw, 16).astype(np.int64)
+
     if a.isolated:
         scrub = torch.empty(192 << 20, dtype=torch.uint8, device=dev)
         scrub.fill_(1)
         torch.cuda.synchronize()
+        L.qs_debug_set_slot(1)
         envs[0].step(acts[0])
     else:
         for k in range(24):
+            L.qs_debug_set_slot(k & 3)
             envs[k % R].step(acts[k % R])
     torch.cuda.synchronize()
-    L = N.lib()
-    nw = min(n // 32, 8192)
-    buf = np.zeros(nw * 16, np.uint64)
-    rc = L.qs_debug_timeline(buf.ctypes.data_as(C.c_void_p), C.c_int(nw * 16))
-    assert rc == 0, rc
-    t = buf.reshape(nw, 16).astype(np.int64)
+    gaps = None
+    if not a.isolated:      # consecutive launches 20..23 live in slots 0..3: gap = first release of launch k+1 - last exit of launch k
+        tl = [fetch(sl) for sl in range(4)]
+        last = [int(max(x[:, k].max() for k in range(16))) for x in tl]
+        gaps = {"last_exit_to_next_release_us": [round((int(tl[k + 1][:, 1].min()) - last[k]) / 1e3, 2) for k in range(3)],
+                "release_to_release_us": [round((int(tl[k + 1][:, 1].min()) - int(tl[k][:, 1].min())) / 1e3, 2) for k in range(3)],
+                "next_first_start_minus_last_exit_us": [round((int(tl[k + 1][:, 0].min()) - last[k]) / 1e3, 2) for k in range(3)]}
+    t = fetch(1 if a.isolated else 3)
     used = [k for k in range(16) if (t[:, k] > 0).all()]
     t = t[:, used]
     t0 = t[:, 0].min()
@@ -86,6 +99,7 @@ def main():
     d = np.diff(rel, axis=1)
     out["per_warp_durations_us_median"] = {names[k] + "->" + names[k + 1]: round(float(np.median(d[:, k])), 2) for k in range(len(names) - 1)}
     out["span_us"] = round(float(rel[:, -1].max()), 2)
+    out["gaps"] = gaps
     out["release_to_last_exit_us"] = round(float(rel[:, -1].max() - rel[:, 1].min()), 2)
     print(json.dumps(out))
 
