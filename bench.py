@@ -523,6 +523,28 @@ def run_extras(a, envs, acts, gen, dev, world, R, peak_gbs, barrier):
         del ro, hold
     except Exception as ex:  # pragma: no cover
         extras["fused_rollout_T32"] = {"error": repr(ex)}
+    # policy + env in ONE launch: the SB3-MlpPolicy-shaped actor (+ critic) evaluated inside qs_rollout every tick
+    try:
+        from gym_pybullet_drones_b200.policy import MlpPolicy
+        T = 16
+        for name, critic in (("actor_only", False), ("actor_critic", True)):
+            pol = MlpPolicy.random(D * OBS_DIM, D * A, seed=3, critic=critic, device=dev)
+            noise = torch.randn((T, DRONES_PER_GPU // D, D * A), device=dev, generator=gen)
+            hold = [envs[0].rollout(policy=pol, noise=noise)]
+
+            def prol(n):
+                for k in range(n):
+                    hold[0] = envs[k % R].rollout(policy=pol, noise=noise, out=hold[0])
+
+            pms = timed(prol, 10) / T
+            macs = (D * OBS_DIM * 64 + 64 * 64 + 64 * D * A) + ((D * OBS_DIM * 64 + 64 * 64 + 64) if critic else 0)
+            extras["policy_rollout_" + name] = {"ms_per_tick": pms, "value": DRONES_PER_GPU * world / (pms * 1e-3), "unit": METRIC,
+                                                 "mlp_tflops_fp32": 2 * macs * (DRONES_PER_GPU // D) / (pms * 1e-3) / 1e12,
+                                                 "note": "qs_rollout(policy=MlpPolicy %d-64-64-%d%s): FP32 FFMA inside the rollout kernel, T=%d ticks per launch" % (D * OBS_DIM, D * A, " + critic" if critic else "", T)}
+            del hold, noise, pol
+    except Exception as ex:  # pragma: no cover
+        extras["policy_rollout"] = {"error": repr(ex)}
+        torch.cuda.synchronize()
     # BASELINE configs[1]: 4096 x HoverAviary with the embedded DSLPIDControl (act=PID): per-launch (launch-latency bound) and
     # through the fused rollout, where the launch cost is paid once per 32 ticks
     try:

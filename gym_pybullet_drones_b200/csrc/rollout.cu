@@ -15,10 +15,111 @@ struct RolloutArgs {
     QsParams P;
     QsState st;
     QsRolloutIO io;
+    QsPolicy pol;        // copy of *io.policy (device pointers inside) when POLICY
     int act_type, task, n_envs, D, substeps, N, A, obs_dim, tpb;
     unsigned effects, flags;
     int stage_mode, cap;
 };
+
+// ---- on-device policy: SB3-MlpPolicy-shaped MLP evaluated by ONE WARP per network (warp 0 actor, warp 1 critic) ---------------
+constexpr int kHid = 64, kHidStride = 68;      // hidden rows padded to 68 floats: conflict-free 128-bit reads across 8 rows
+
+__device__ __forceinline__ float4 ld4_any(const float* p, bool vec) {
+    if (vec) return *reinterpret_cast<const float4*>(p);
+    return make_float4(p[0], p[1], p[2], p[3]);
+}
+
+// y[av][0..63] = act(b + W^T x[av]) for av < n_av (n_av <= 32).  x rows: K floats at stride x_stride in shared memory; W [K][64]
+// row-major in global memory (read through L1: every lane group of a warp and every CTA of the SM reads the same 8 KB..37 KB).
+// Lane = (aviary group ag = lane / 8, unit group ug = lane % 8): 8 aviaries (ag + 4 j) x 8 units (8 ug + u) = 64 accumulators;
+// per 4 k: 8 x-loads + 8 weight loads for 256 FFMA.  May run in place (y_s == x_s, same stride): all reads precede all writes.
+template <bool TANH>
+__device__ __forceinline__ void mlp_layer64(const float* x_s, int x_stride, int K, bool x_vec, const float* __restrict__ W,
+                                            const float* __restrict__ b, float* y_s, int n_av, int lane) {
+    const int ag = lane >> 3, ug = lane & 7;
+    float acc[8][8];
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + 8 * ug)), b1 = __ldg(reinterpret_cast<const float4*>(b + 8 * ug + 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            acc[j][0] = b0.x; acc[j][1] = b0.y; acc[j][2] = b0.z; acc[j][3] = b0.w;
+            acc[j][4] = b1.x; acc[j][5] = b1.y; acc[j][6] = b1.z; acc[j][7] = b1.w;
+        }
+    }
+    const int K4 = K & ~3;
+    for (int k = 0; k < K4; k += 4) {
+        float4 xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int av = ag + 4 * j;
+            xv[j] = av < n_av ? ld4_any(x_s + (size_t)av * x_stride + k, x_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(k + kk) * kHid + 8 * ug));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(k + kk) * kHid + 8 * ug + 4));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float x = kk == 0 ? xv[j].x : (kk == 1 ? xv[j].y : (kk == 2 ? xv[j].z : xv[j].w));
+                acc[j][0] = fmaf(x, w0.x, acc[j][0]); acc[j][1] = fmaf(x, w0.y, acc[j][1]);
+                acc[j][2] = fmaf(x, w0.z, acc[j][2]); acc[j][3] = fmaf(x, w0.w, acc[j][3]);
+                acc[j][4] = fmaf(x, w1.x, acc[j][4]); acc[j][5] = fmaf(x, w1.y, acc[j][5]);
+                acc[j][6] = fmaf(x, w1.z, acc[j][6]); acc[j][7] = fmaf(x, w1.w, acc[j][7]);
+            }
+        }
+    }
+    for (int k = K4; k < K; ++k) {                        // K not a multiple of 4 (A = 1 observations)
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)k * kHid + 8 * ug));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)k * kHid + 8 * ug + 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int av = ag + 4 * j;
+            const float x = av < n_av ? x_s[(size_t)av * x_stride + k] : 0.f;
+            acc[j][0] = fmaf(x, w0.x, acc[j][0]); acc[j][1] = fmaf(x, w0.y, acc[j][1]);
+            acc[j][2] = fmaf(x, w0.z, acc[j][2]); acc[j][3] = fmaf(x, w0.w, acc[j][3]);
+            acc[j][4] = fmaf(x, w1.x, acc[j][4]); acc[j][5] = fmaf(x, w1.y, acc[j][5]);
+            acc[j][6] = fmaf(x, w1.z, acc[j][6]); acc[j][7] = fmaf(x, w1.w, acc[j][7]);
+        }
+    }
+    __syncwarp();                                         // in-place layers: every read of x precedes the first write of y
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int av = ag + 4 * j;
+        if (av < n_av) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = TANH ? tanhf(acc[j][u]) : acc[j][u];
+            float4* y = reinterpret_cast<float4*>(y_s + (size_t)av * kHidStride + 8 * ug);
+            y[0] = make_float4(v[0], v[1], v[2], v[3]); y[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    __syncwarp();
+}
+
+// out[av][j] = b[j] + sum_k h[av][k] W[k][j], j < n_out: lane = aviary, the weights are warp-uniform loads
+__device__ __forceinline__ void mlp_head(const float* h_s, const float* __restrict__ W, const float* __restrict__ b, int n_out,
+                                         float* out_s, int n_av, int lane) {
+    if (lane >= n_av) return;
+    const float* h = h_s + (size_t)lane * kHidStride;
+    for (int j0 = 0; j0 < n_out; j0 += 4) {
+        const int nj = n_out - j0 < 4 ? n_out - j0 : 4;
+        float a0 = __ldg(b + j0), a1 = nj > 1 ? __ldg(b + j0 + 1) : 0.f, a2 = nj > 2 ? __ldg(b + j0 + 2) : 0.f, a3 = nj > 3 ? __ldg(b + j0 + 3) : 0.f;
+        for (int k = 0; k < kHid; k += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(h + k);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float x = kk == 0 ? hv.x : (kk == 1 ? hv.y : (kk == 2 ? hv.z : hv.w));
+                const float* w = W + (size_t)(k + kk) * n_out + j0;
+                a0 = fmaf(x, __ldg(w), a0);
+                if (nj > 1) a1 = fmaf(x, __ldg(w + 1), a1);
+                if (nj > 2) a2 = fmaf(x, __ldg(w + 2), a2);
+                if (nj > 3) a3 = fmaf(x, __ldg(w + 3), a3);
+            }
+        }
+        float* o = out_s + (size_t)lane * n_out + j0;
+        o[0] = a0; if (nj > 1) o[1] = a1; if (nj > 2) o[2] = a2; if (nj > 3) o[3] = a3;
+    }
+}
 
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -36,8 +137,8 @@ __device__ __forceinline__ void round_to_planes(qs::Drone& d) {
     d.qx = __dmul_rn(d.qx, inv); d.qy = __dmul_rn(d.qy, inv); d.qz = __dmul_rn(d.qz, inv); d.qw = __dmul_rn(d.qw, inv);
 }
 
-template <int EFF, bool PIDACT>
-__global__ void __launch_bounds__(kMaxTPB, 4) rollout_kernel(const __grid_constant__ RolloutArgs a) {
+template <int EFF, bool PIDACT, bool POLICY>
+__global__ void __launch_bounds__(POLICY ? 64 : kMaxTPB, POLICY ? 3 : 4) rollout_kernel(const __grid_constant__ RolloutArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QsParams& P = a.P;
     const int tpb = a.tpb, D = a.D, A = a.A, od = a.obs_dim, T = a.io.T;
@@ -55,6 +156,11 @@ __global__ void __launch_bounds__(kMaxTPB, 4) rollout_kernel(const __grid_consta
     unsigned char* done_s = oob_s + cap;
     unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(smem_raw + fixed - 16);
     float* stage_s = reinterpret_cast<float*>(smem_raw + fixed);                       // [tpb*od + (T+1)*A] sliding window
+    // POLICY: [2 nets][32 aviaries][68] hidden activations, [32][out_dim] means, [32] values, [tpb] log-prob terms, after the window
+    float* pol_s = stage_s + ((((size_t)tpb * od + (size_t)(T + 1) * A) + 3) & ~(size_t)3);
+    float* mean_s = pol_s + 2 * 32 * kHidStride;                                        // [<= 128 aviaries][out_dim]
+    float* val_s = mean_s + (size_t)kMaxTPB * a.pol.out_dim;
+    float* lp_s = val_s + kMaxTPB;
 
     const long long e = live ? i / D : 0;
     const int le = t / D;
@@ -90,8 +196,54 @@ __global__ void __launch_bounds__(kMaxTPB, 4) rollout_kernel(const __grid_consta
     for (int k = 0; k < T; ++k) {
         // ---- this tick's action: caller-provided or generated on the device --------------------------------------
         float act[4] = {0.f, 0.f, 0.f, 0.f};
+        float raw_act[4] = {0.f, 0.f, 0.f, 0.f};
+        if (POLICY) {
+            // the aviaries of this CTA: rows [le D, le D + D) of the window = one flattened observation of in_dim floats each
+            const int n_av = rows / D, warp = t >> 5, lane = t & 31;
+            const bool x_vec = (A == 4) && ((a.pol.in_dim & 3) == 0);
+            for (int a0 = 0; a0 < n_av; a0 += 32) {           // 32 aviaries per pass (one pass for D >= 2)
+                const int na = n_av - a0 < 32 ? n_av - a0 : 32;
+                const float* x0 = base + (size_t)a0 * a.pol.in_dim;
+                if (warp == 0) {
+                    float* h = pol_s;
+                    mlp_layer64<true>(x0, a.pol.in_dim, a.pol.in_dim, x_vec, a.pol.w1, a.pol.b1, h, na, lane);
+                    mlp_layer64<true>(h, kHidStride, kHid, true, a.pol.w2, a.pol.b2, h, na, lane);
+                    mlp_head(h, a.pol.w3, a.pol.b3, a.pol.out_dim, mean_s + (size_t)a0 * a.pol.out_dim, na, lane);
+                } else if (warp == 1 && a.pol.vw1) {
+                    float* h = pol_s + 32 * kHidStride;
+                    mlp_layer64<true>(x0, a.pol.in_dim, a.pol.in_dim, x_vec, a.pol.vw1, a.pol.vb1, h, na, lane);
+                    mlp_layer64<true>(h, kHidStride, kHid, true, a.pol.vw2, a.pol.vb2, h, na, lane);
+                    mlp_head(h, a.pol.vw3, a.pol.vb3, 1, val_s + a0, na, lane);
+                }
+            }
+            __syncthreads();
+            float lp = 0.f;
+            if (live) {
+                const int od_out = a.pol.out_dim;
+                for (int j = 0; j < A; ++j) {
+                    const int idx = dslot * A + j;
+                    const float ls = __ldg(a.pol.log_std + idx);
+                    const float eps = a.pol.noise ? __ldg(a.pol.noise + ((long long)k * E + e) * od_out + idx) : 0.f;
+                    const float r = fmaf(expf(ls), eps, mean_s[le * od_out + idx]);
+                    raw_act[j] = r;
+                    act[j] = fminf(fmaxf(r, -1.f), 1.f);                             // the env clips to its action space
+                    lp += -0.5f * eps * eps - ls - 0.91893853320467274f;            // log N(r; mean, std)
+                }
+                lp_s[t] = lp;
+            }
+            __syncthreads();
+            if (live && dslot == 0) {
+                float s_lp = 0.f;
+                for (int q = 0; q < D; ++q) s_lp += lp_s[t + q];
+                const long long oe = (long long)k * E + e;
+                if (a.pol.logprob) a.pol.logprob[oe] = s_lp;
+                if (a.pol.values && a.pol.vw1) a.pol.values[oe] = val_s[le];
+            }
+        }
         if (live) {
-            if (a.io.actions) {
+            if (POLICY) {
+                // (act / raw_act set above)
+            } else if (a.io.actions) {
                 const float* ap = a.io.actions + ((long long)k * N + i) * A;
                 if (A == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(ap)); act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w; }
                 else if (A == 3) { act[0] = __ldg(ap); act[1] = __ldg(ap + 1); act[2] = __ldg(ap + 2); }
@@ -110,9 +262,10 @@ __global__ void __launch_bounds__(kMaxTPB, 4) rollout_kernel(const __grid_consta
             else tail[0] = act[0];
             if (a.io.actions_out) {
                 float* ao = a.io.actions_out + ((long long)k * N + i) * A;
-                if (A == 4) *reinterpret_cast<float4*>(ao) = make_float4(act[0], act[1], act[2], act[3]);
-                else if (A == 3) { ao[0] = act[0]; ao[1] = act[1]; ao[2] = act[2]; }
-                else ao[0] = act[0];
+                const float* av = POLICY ? raw_act : act;                        // PPO stores the unclipped sample
+                if (A == 4) *reinterpret_cast<float4*>(ao) = make_float4(av[0], av[1], av[2], av[3]);
+                else if (A == 3) { ao[0] = av[0]; ao[1] = av[1]; ao[2] = av[2]; }
+                else ao[0] = av[0];
             }
         }
         // ---- physics ---------------------------------------------------------------------------------------------
@@ -283,17 +436,36 @@ int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int 
         a.stage_mode = (aligned && A == 4) ? 1 : 2;
     }
     const int blocks = (int)((a.N + a.tpb - 1) / a.tpb);
-    const int threads = ((a.tpb + 31) / 32) * 32;
-    const size_t sm = smem_fixed(a.cap) + (size_t)a.tpb * a.obs_dim * 4 + (size_t)(io->T + 1) * A * 4 + 32;
+    int threads = ((a.tpb + 31) / 32) * 32;
+    size_t sm = smem_fixed(a.cap) + (size_t)a.tpb * a.obs_dim * 4 + (size_t)(io->T + 1) * A * 4 + 32;
     cudaStream_t s = (cudaStream_t)stream;
+    if (io->policy) {
+        const QsPolicy& q = *io->policy;
+        if (pid_act || (effects & 7u) || a.cap > 64) return fail(QS_ERR_UNSUPPORTED, "qs_rollout: the on-device policy supports RPM / ONE_D_RPM actions, no DYN+ effects, drones_per_env <= 64");
+        if (io->actions) return fail(QS_ERR_UNSUPPORTED, "qs_rollout: pass either actions or a policy");
+        if (!q.w1 || !q.b1 || !q.w2 || !q.b2 || !q.w3 || !q.b3 || !q.log_std) return fail(QS_ERR_NULL, "qs_rollout: policy weights are NULL");
+        if (q.in_dim != drones_per_env * a.obs_dim || q.out_dim != drones_per_env * A) return fail(QS_ERR_SIZE, "qs_rollout: policy in_dim/out_dim must be D*obs_dim / D*A");
+        if (q.vw1 && (!q.vb1 || !q.vw2 || !q.vb2 || !q.vw3 || !q.vb3)) return fail(QS_ERR_NULL, "qs_rollout: incomplete critic");
+        if (q.values && !q.vw1) return fail(QS_ERR_NULL, "qs_rollout: values requested without a critic");
+        for (const float* w : {q.w1, q.b1, q.w2, q.b2, q.vw1, q.vb1, q.vw2, q.vb2})
+            if (w && !aligned16(w)) return fail(QS_ERR_ALIGN, "qs_rollout: policy matrices must be 16-byte aligned");
+        a.pol = q;
+        threads = 64;                                            // warp 0: actor, warp 1: critic
+        sm += 16 + (size_t)(2 * 32 * kHidStride + kMaxTPB * q.out_dim + 2 * kMaxTPB) * 4;
+        if (sm > 200 * 1024) return fail(QS_ERR_UNSUPPORTED, "qs_rollout: policy + window exceed shared memory");
+        if (sm > 48 * 1024) cudaFuncSetAttribute(rollout_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        rollout_kernel<0, false, true><<<blocks, threads, sm, s>>>(a);
+        const cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : cuda_fail(e, "qs_rollout (policy) launch");
+    }
 #define QS_RCASE(E)                                                                                                   \
     case E: {                                                                                                         \
         if (pid_act) {                                                                                                \
-            if (sm > 48 * 1024) cudaFuncSetAttribute(rollout_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStepSmemFixed + kStageLimit + 32)); \
-            rollout_kernel<E, true><<<blocks, threads, sm, s>>>(a);                                                   \
+            if (sm > 48 * 1024) cudaFuncSetAttribute(rollout_kernel<E, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStepSmemFixed + kStageLimit + 32)); \
+            rollout_kernel<E, true, false><<<blocks, threads, sm, s>>>(a);                                            \
         } else {                                                                                                      \
-            if (sm > 48 * 1024) cudaFuncSetAttribute(rollout_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStepSmemFixed + kStageLimit + 32)); \
-            rollout_kernel<E, false><<<blocks, threads, sm, s>>>(a);                                                  \
+            if (sm > 48 * 1024) cudaFuncSetAttribute(rollout_kernel<E, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStepSmemFixed + kStageLimit + 32)); \
+            rollout_kernel<E, false, false><<<blocks, threads, sm, s>>>(a);                                           \
         }                                                                                                             \
     } break;
     switch (effects & 7u) { QS_RCASE(0) QS_RCASE(1) QS_RCASE(2) QS_RCASE(3) QS_RCASE(4) QS_RCASE(5) QS_RCASE(6) QS_RCASE(7) }

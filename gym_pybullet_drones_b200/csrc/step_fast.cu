@@ -87,8 +87,10 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
             pf(a.st.planes + 4 * w0, nb); pf(a.st.planes + 4 * (N + w0), nb); pf(a.st.planes + 4 * (2 * N + w0), nb);
             if (((rows * 8) & 15) == 0) pf(a.st.planes + 12 * N + w0, (unsigned)rows * 8u);
             if (((rows * A * 4) & 15) == 0) pf(a.io.action + w0 * A, (unsigned)(rows * A * 4));
-            if (a.prefetch > 1) pf(span_src, span_bytes);      // (the history follows the state loads through the bulk copy: prefetching
-        }                                                      //  it too delays the state of an isolated launch, measured)
+            // the history too (default): back-to-back launches then find it in L2 and write it back during the FP64 loop (-0.5 us
+            // per step); a launch on an idle GPU has no window and pays ~2 us because its state loads queue behind it (measured)
+            if (a.prefetch > 1) pf(span_src, span_bytes);
+        }
     }
     __syncwarp();
     // read-only tables (never written by a kernel): safe ahead of the dependency wait
@@ -116,9 +118,23 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
     // state loads issued just before it -- has ARRIVED: warps issue in order, so the comparison below stalls until then, and
     // the memory system serves every warp's 120 bytes of state ahead of the 19 MB of history the physics does not need yet.
     // (The comparison is always true for a valid counter; the compiler cannot know.)
+    // Experiment (QS_ROW_LOADS=1, off): every lane fetches only the history of its own row, leaving the 48-byte head and the
+    // dropped oldest action (64 of 288 bytes per row) in HBM.  32 small bulk copies per warp measured SLOWER than one copy of
+    // the whole span (13.2 vs 12.3 us per step): the default moves the span.
+    const bool by_rows = A == 4 && a.row_loads;
+    auto load_span = [&]() {
+        if (by_rows) {
+            const unsigned hb = (unsigned)(od - 16) * 4u;
+            if (lane == 0) mbar_expect_tx(bar, hb * (unsigned)rows);
+            __syncwarp();
+            if (live) bulk_g2s(xs + (size_t)lane * od + 16, span_src + (size_t)lane * od + 16, hb, bar);
+        } else if (lane == 0) {
+            tma_bulk_g2s(xs, span_src, span_bytes, bar);
+        }
+    };
     bool issued = false;
     if (a.flags_late_tma == 0 || __shfl_sync(0xffffffffu, sc, 0) != (int)0x80000000) {
-        if (lane == 0) tma_bulk_g2s(xs, span_src, span_bytes, bar);
+        load_span();
         issued = true;
     }
     QS_STAMP(2);
@@ -213,7 +229,7 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
     QS_STAMP(6);
 
     // ---- observation rows --------------------------------------------------------------------------------------------------------
-    if (!issued && lane == 0) tma_bulk_g2s(xs, span_src, span_bytes, bar);
+    if (!issued) load_span();
     const unsigned fin_rows = want_fin ? __ballot_sync(0xffffffffu, reset_me && live) : 0u;
     // Fused observation gather: the finished rows go a second time, straight from shared memory, to the learner's tensor
     // (peer memory over NVLink), the per-aviary outputs with them; the last warp of the grid raises the learner's flag.

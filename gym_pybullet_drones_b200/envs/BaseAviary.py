@@ -81,6 +81,7 @@ class BaseAviary(Env):
                  autoreset_clears_action_buffer=False,
                  rpy_f32=True,
                  host_copy=True,
+                 track_last_action=None,
                  ):
         """Same positional/keyword parameters as the reference (BaseAviary.py:25-40).
 
@@ -98,6 +99,9 @@ class BaseAviary(Env):
         rpy_f32 : bool
             Evaluate the reported roll/pitch/yaw with float32 atan2f/asinf on float64 arguments (default; error ~2e-7 rad,
             far inside the 1e-5 parity bound); False = float64 atan2/asin.
+        track_last_action : bool | None
+            Keep `last_clipped_action` (BaseAviary.py:372, 32 bytes written per drone and tick).  None = only where the model
+            needs it (drag, CtrlAviary/VelocityAviary state vectors, formations) or for the single-env API.
         host_copy : bool
             NumPy mode only: return fresh arrays (True) or views of the pinned staging buffers
             that stay valid until the next-but-one step (False).
@@ -166,6 +170,7 @@ class BaseAviary(Env):
                 self._flags &= ~(N.FLAG_AUTORESET_SAME_STEP | N.FLAG_AUTORESET_NEXT_STEP)
         self.metadata = dict(self.metadata, autoreset_mode=self.autoreset_mode)
         self._host_copy = host_copy
+        self._track_last_action = track_last_action
         self._log = None                     # (QsLogRing, controls tensor) while a utils.Logger is attached
         self._gather = None                  # sharding.ObsGather: the tick also writes its rows into the learner's tensor
         #### Initial poses (BaseAviary.py:194-207); [D,3] shared by all aviaries or [E,D,3] per aviary ####
@@ -289,7 +294,11 @@ class BaseAviary(Env):
         tp.update(self._task_params())
         self._P = fill_params(self._consts, **tp)
         st = N.QsState()
-        st.planes, st.last_rpm = self._planes.data_ptr(), self._last_rpm.data_ptr()
+        track = self._track_last_action
+        if track is None:
+            track = (not self.VECTORIZED) or raw or bool(self._effects & N.EFFECT_DRAG) or big_dw
+        self._track_last_action = bool(track)
+        st.planes, st.last_rpm = self._planes.data_ptr(), (self._last_rpm.data_ptr() if track else None)
         st.step_counter, st.pending_reset = self._step_counter.data_ptr(), self._pending.data_ptr()
         st.pid = self._pid.data_ptr() if self._pid is not None else None
         st.init_pos, st.init_quat = self._init_pos.data_ptr(), self._init_quat.data_ptr()
@@ -398,6 +407,8 @@ class BaseAviary(Env):
 
     @property
     def last_clipped_action(self):
+        if not self._track_last_action:
+            raise AttributeError("last_clipped_action is not tracked by this env (pass track_last_action=True)")
         return self._last_rpm.view(self._E, self._D, 4) if self.VECTORIZED else self._host(self._last_rpm)
 
     @staticmethod

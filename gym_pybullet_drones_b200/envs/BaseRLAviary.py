@@ -90,7 +90,7 @@ class BaseRLAviary(BaseAviary):
 
     ################################################################################
 
-    def rollout(self, actions=None, num_steps=None, seed=0, out=None):
+    def rollout(self, actions=None, num_steps=None, seed=0, out=None, policy=None, noise=None):
         """T control ticks in one kernel launch (qs_rollout): exactly `num_steps` calls of `step()` with the same
         actions, but the drone state stays in registers and the action history in shared memory between ticks.
 
@@ -98,7 +98,13 @@ class BaseRLAviary(BaseAviary):
         device from (`seed`, tick, drone) -- the synthetic random-action workload.  Autoreset must be "same_step" or
         disabled; `info["final_obs"]` is not produced.  Returns a dict of CUDA tensors in rollout-buffer layout:
         obs [T, E, D, obs_dim] (observation AFTER each tick), actions [T, E, D, A], rewards / terminated / truncated [T, E].
-        `out` may pass a previous result dict to reuse its buffers."""
+        `out` may pass a previous result dict to reuse its buffers.
+
+        `policy` (a `gym_pybullet_drones_b200.policy.MlpPolicy`): the actions of every tick come from the policy evaluated
+        INSIDE the kernel on the current observation -- SB3 `collect_rollouts` (examples/learn.py:93) without a policy launch
+        or an action tensor per tick.  `noise` [T, E, D*A] standard-normal draws (None = act deterministically).  The result
+        then also holds `log_probs` [T, E] and, with a critic, `values` [T, E]; `actions` are the UNCLIPPED samples (what PPO
+        stores), the env applied them clipped to [-1, 1]."""
         if not self.VECTORIZED:
             raise ValueError("rollout() needs the vector API (num_envs=...)")
         if self._flags & N.FLAG_AUTORESET_NEXT_STEP:
@@ -106,6 +112,16 @@ class BaseRLAviary(BaseAviary):
         if self._dw_fz is not None:
             raise ValueError("rollout() needs drones_per_env <= 128")
         E, D, A, od, dev = self._E, self._D, self._A, self._obs_dim, self.device
+        if policy is not None:
+            if actions is not None:
+                raise ValueError("pass either actions or a policy")
+            if policy.in_dim != D * od or policy.out_dim != D * A:
+                raise ValueError("policy must map %d inputs to %d outputs" % (D * od, D * A))
+            if noise is not None:
+                noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+                if noise.numel() % (E * D * A) or (num_steps is not None and noise.numel() != int(num_steps) * E * D * A):
+                    raise ValueError("noise must be [T, %d, %d]" % (E, D * A))
+                num_steps = noise.numel() // (E * D * A)
         if actions is not None:
             actions = actions.to(device=dev, dtype=torch.float32).contiguous()
             T = actions.shape[0]
@@ -121,6 +137,11 @@ class BaseRLAviary(BaseAviary):
                        truncated=torch.empty((T, E), dtype=torch.bool, device=dev))
         elif actions is not None:
             out["actions"] = actions
+        if policy is not None:
+            if "log_probs" not in out:
+                out["log_probs"] = torch.empty((T, E), dtype=torch.float32, device=dev)
+            if policy.critic is not None and "values" not in out:
+                out["values"] = torch.empty((T, E), dtype=torch.float32, device=dev)
         tmax = self._lib.qs_rollout_max_ticks(self._act_type(), self._B, D)
         if tmax <= 0:
             raise ValueError("rollout() is not available for this observation width (action buffer too long for shared memory)")
@@ -141,6 +162,11 @@ class BaseRLAviary(BaseAviary):
                 io.reward, io.terminated, io.truncated = out["rewards"][k0].data_ptr(), out["terminated"][k0].data_ptr(), out["truncated"][k0].data_ptr()
                 io.done = None
                 io.tick0, io.T = int(getattr(self, "_rollout_tick", 0)) + k0, tt
+                if policy is not None:
+                    qp = policy.c_struct(None if noise is None else noise.view(T, -1)[k0], out["log_probs"][k0],
+                                         out["values"][k0] if policy.critic is not None else None)
+                    io.policy = C.addressof(qp)
+                    io.actions, io.actions_out = None, out["actions"][k0].data_ptr()
                 rc = self._lib.qs_rollout(C.byref(self._P), C.byref(self._st), C.byref(io), self._act_type(), self._task(),
                                           E, D, self.PYB_STEPS_PER_CTRL, self._effects,
                                           self._flags & ~N.FLAG_AUTORESET_NEXT_STEP, stream)

@@ -174,6 +174,23 @@ typedef struct QsStepIO {
 /* Spins (bounded, ~2 s, then *err_flag = 1) until flags[r] - seq >= 0 for every r < world: the learner side of obs_gather. */
 int qs_wait_flags(const unsigned* flags, unsigned seq, int world, unsigned* err_flag, void* stream);
 
+/* On-device policy for qs_rollout (the caller is SB3's collect_rollouts, examples/learn.py:67-95): an
+ * SB3-MlpPolicy-shaped actor -- flatten(the aviary's [D][obs_dim] observation) -> 64 tanh -> 64 tanh -> linear mean, state
+ * independent log_std, Gaussian sample, clip to [-1, 1] for the env -- and optionally the critic (same shape, 1 output),
+ * evaluated inside the rollout kernel from the observation window in shared memory (FP32 FFMA, weights through L1).
+ * Weight matrices are row-major [in][out] float32 (torch.nn.Linear.weight transposed), device pointers. */
+typedef struct QsPolicy {
+    const float *w1, *b1;      /* [in_dim][64], [64]   in_dim = D * obs_dim */
+    const float *w2, *b2;      /* [64][64], [64] */
+    const float *w3, *b3;      /* [64][out_dim], [out_dim]   out_dim = D * A */
+    const float* log_std;      /* [out_dim] */
+    const float *vw1, *vb1, *vw2, *vb2, *vw3, *vb3;   /* critic [in_dim][64], [64][64], [64][1]; all NULL = no critic */
+    const float* noise;        /* [T][E][out_dim] standard-normal draws (e.g. torch.randn), or NULL: action = mean */
+    float* logprob;            /* out [T][E] log-probability of the sampled (unclipped) action; nullable */
+    float* values;             /* out [T][E] critic output; nullable (required NULL without a critic) */
+    int in_dim, out_dim;
+} QsPolicy;
+
 /* Multi-tick rollout: T control ticks in ONE launch (the caller is SB3's collect_rollouts,
  * examples/learn.py:93).  Exactly T calls of qs_step with SAME_STEP (or no) autoreset, but the drone state stays in
  * registers and the action history in shared memory between ticks: per tick only the action is read and the observation
@@ -192,6 +209,9 @@ typedef struct QsRolloutIO {
     long long tick0;            /* global index of the first tick of this launch (continues the generator's stream) */
     int T;                      /* ticks in this launch; qs_rollout_max_ticks() bounds it (shared-memory window) */
     int act_buffer_size;        /* B */
+    const QsPolicy* policy;     /* optional (HOST pointer): the actions come from this policy evaluated on the current observation;
+                                   `actions` must then be NULL, actions_out receives the sampled, UNCLIPPED actions (what PPO
+                                   stores), the env applies them clipped to [-1, 1].  RPM / ONE_D_RPM, no DYN+ effects, hidden 64. */
 } QsRolloutIO;
 
 /* Host-buffer variant of one control tick (what a CPU-side caller such as SB3's DummyVecEnv loop sees): pinned host

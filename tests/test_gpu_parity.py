@@ -597,3 +597,136 @@ def test_autoreset_can_clear_action_buffer_and_controllers(mode):
     assert n_resets > E // 2
     pid_dev = env._pid.view(9, E).cpu().numpy()
     assert relerr(pid_dev[0:3].T, ora.ctrl.integral_pos_e) < RTOL and relerr(pid_dev[6:9].T, ora.ctrl.integral_rpy_e) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (d) BASELINE configs at their full sizes against the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def test_config3_full_size_65536_drones_125_ticks_vs_oracle():
+    """BASELINE configs[2] at size: 32768 x MultiHover D=2 = 65536 drones, random actions, 125 ticks x 8 substeps = 1000
+    physics steps, every element of the kinematic state against the float64 oracle (the port needs ~20 s for this)."""
+    _, _, _, MultiHoverAviary, ActionType, _, Physics, O = _imports()
+    E, D, T = 32768, 2, 125
+    rng = np.random.default_rng(2024)
+    env = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E)
+    ora = O.OracleAviary("multihover", E, D, act="rpm")
+    env.reset(); ora.reset()
+    for t in range(T):
+        a = rng.uniform(-1, 1, (E, D, 4)).astype(np.float32)
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(a).cuda())
+        o_obs, o_rew, o_term, o_trunc = ora.step(a)
+        if t % 25 == 24 or t == T - 1:
+            st = state_of(env)
+            assert relerr(st["pos"], ora.pos) < TIGHT and quat_err(st["quat"], ora.quat) < TIGHT, t
+            assert relerr(st["vel"], ora.vel) < TIGHT and relerr(st["rpy_rates"], ora.rpy_rates) < TIGHT, t
+            assert relerr(obs.cpu().numpy()[..., 6:], o_obs[..., 6:]) < OBS_TOL and relerr(rew.cpu().numpy(), o_rew) < OBS_TOL, t
+            assert np.array_equal(term.cpu().numpy(), o_term)
+            clear = ~_borderline(ora)
+            assert np.array_equal(trunc.cpu().numpy()[clear], o_trunc[clear]), t
+
+
+def test_config2_pid_4096_30hz_teacher_forced_vs_oracle():
+    """BASELINE configs[1] as written: 4096 x HoverAviary with the embedded DSLPIDControl (act=PID) at the RL default
+    240/30 Hz (S=8).  The 30 Hz loop is chaotic in the reference itself, so every tick restarts from the ORACLE's previous
+    state (kinematics + controller integrals), exactly like the reference-golden teacher-forced test, but at E=4096."""
+    _, _, HoverAviary, _, ActionType, _, Physics, O = _imports()
+    E, T = 4096, 40
+    g = torch.Generator().manual_seed(0)
+    sp = (torch.tensor([-0.5, -0.5, 0.5]) + torch.rand((E, 1, 3), generator=g)).numpy().astype(np.float32)
+    env = HoverAviary(physics=Physics.DYN, act=ActionType.PID, pyb_freq=240, ctrl_freq=30, num_envs=E)
+    ora = O.OracleAviary("hover", E, 1, act="pid", ctrl_freq=30)
+    env.reset(); ora.reset()
+    for t in range(T):
+        if t > 0:
+            env.set_state(pos=ora.pos, quat=ora.quat, vel=ora.vel, rpy_rates=ora.rpy_rates, step_counter=ora.step_counter)
+            env._pid[0:3] = torch.from_numpy(ora.ctrl.integral_pos_e.T.copy()).cuda()
+            env._pid[3:6] = torch.from_numpy(ora.ctrl.last_rpy.T.copy()).cuda()
+            env._pid[6:9] = torch.from_numpy(ora.ctrl.integral_rpy_e.T.copy()).cuda()
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(sp).cuda())
+        o_obs, o_rew, o_term, o_trunc = ora.step(sp)
+        st = state_of(env)
+        for f in ("pos", "quat", "vel", "rpy_rates"):
+            e = quat_err(st[f], getattr(ora, f)) if f == "quat" else relerr(st[f], getattr(ora, f))
+            assert e < 1e-7, (f, t, e)
+        pid = env._pid.cpu().numpy()
+        assert relerr(pid[0:3].T, ora.ctrl.integral_pos_e) < 1e-9 and relerr(pid[3:6].T, ora.ctrl.last_rpy) < 1e-9, t
+        assert relerr(pid[6:9].T, ora.ctrl.integral_rpy_e) < 1e-7, t
+
+
+def _chunked_downwash(O, xyz, chunk=1024):
+    P = O.OracleParams()
+    out = np.zeros(len(xyz))
+    pos = xyz[None]
+    for s in range(0, len(xyz), chunk):                     # rows [s, s+chunk) against every source: O(N^2) in pieces
+        rows = pos[:, s:s + chunk]
+        dz = pos[:, None, :, 2] - rows[:, :, None, 2]
+        dxy = np.sqrt((pos[:, None, :, 0] - rows[:, :, None, 0]) ** 2 + (pos[:, None, :, 1] - rows[:, :, None, 1]) ** 2)
+        act = (dz > 0) & (dxy < 10)
+        dzs = np.where(act, dz, 1.0)
+        alpha = P.DW[0] * (P.PROP_RADIUS / (4 * dzs)) ** 2
+        beta = P.DW[1] * dzs + P.DW[2]
+        with np.errstate(divide="ignore", over="ignore", invalid="ignore"):
+            f = -alpha * np.exp(-0.5 * (dxy / beta) ** 2)
+        out[s:s + chunk] = np.sum(np.where(act, f, 0.0), axis=2)[0]
+    return out
+
+
+def test_config4_full_size_16384_static_downwash_vs_oracle():
+    """BASELINE configs[3] geometry at size: 128 x 128 grid, 0.15 m pitch, 16 height levels, one aviary of 16384
+    drones.  The pairwise force of qs_downwash, qs_downwash_boxed and the row-sharded qs_downwash_rows (two halves against
+    the gathered array) against BaseAviary._downwash restated in float64 (evaluated in row chunks)."""
+    import ctypes as C
+    from gym_pybullet_drones_b200 import _native as N
+    _, CtrlAviary, _, _, _, _, Physics, O = _imports()
+    k = np.arange(128 * 128)
+    j, i = np.divmod(k, 128)
+    xyz = np.stack([0.15 * i, 0.15 * j, 0.1 + 0.05 * (k % 16)], axis=1).astype(np.float32).astype(np.float64)
+    D = len(xyz)
+    ref = _chunked_downwash(O, xyz)
+    assert np.count_nonzero(ref) > 0.9 * D
+    env = CtrlAviary(num_drones=D, initial_xyzs=xyz, physics=Physics.PYB_DW, num_envs=1)
+    env.reset()
+    L, sp = N.lib(), torch.cuda.current_stream().cuda_stream
+    fz = torch.zeros(D, device="cuda")
+    N.check(L.qs_downwash(C.byref(env._P), C.byref(env._st), 1, D, fz.data_ptr(), sp), "qs_downwash")
+    a = fz.cpu().numpy().astype(np.float64)
+    assert relerr(a, ref) < RTOL
+    ws = torch.zeros((1, D // 32, 8), device="cuda")
+    fz2 = torch.zeros(D, device="cuda")
+    N.check(L.qs_downwash_boxed(C.byref(env._P), C.byref(env._st), 1, D, ws.data_ptr(), fz2.data_ptr(), sp), "qs_downwash_boxed")
+    assert np.array_equal(fz2.cpu().numpy(), fz.cpu().numpy())                 # same chunks, same order: same bits
+    # row-sharded: the gathered array holds every position + the chunk boxes; each half evaluates its own rows
+    nf = int(L.qs_dw_gathered_floats(D))
+    gathered = torch.zeros(nf, device="cuda")
+    gathered[:4 * D] = env._pos_f32.reshape(-1)
+    N.check(L.qs_dw_boxes(gathered.data_ptr(), D, sp), "qs_dw_boxes")
+    fz3 = torch.zeros(D, device="cuda")
+    half = D // 2
+    for r in range(2):
+        rows = env._pos_f32[r * half:(r + 1) * half]
+        N.check(L.qs_downwash_rows(C.byref(env._P), rows.data_ptr(), half, gathered.data_ptr(), D, None, 0, 0, None,
+                                   fz3[r * half:].data_ptr(), sp), "qs_downwash_rows")
+    assert np.array_equal(fz3.cpu().numpy(), fz.cpu().numpy())
+
+
+def test_rollout_vs_oracle_directly():
+    """qs_rollout (T fused ticks, state in registers, history in a sliding shared-memory window) against the float64 oracle
+    itself -- not only against T calls of qs_step: observations, rewards and flags of every tick, state after the last."""
+    _, _, _, MultiHoverAviary, ActionType, _, Physics, O = _imports()
+    E, D, T = 512, 2, 60
+    rng = np.random.default_rng(31)
+    acts = (0.6 * rng.uniform(-1, 1, (T, E, D, 4))).astype(np.float32)
+    env = MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E)
+    ora = O.OracleAviary("multihover", E, D, act="rpm")
+    env.reset(); ora.reset()
+    out = env.rollout(torch.from_numpy(acts).cuda())
+    obs, rew = out["obs"].cpu().numpy(), out["rewards"].cpu().numpy()
+    te, tr = out["terminated"].cpu().numpy(), out["truncated"].cpu().numpy()
+    for t in range(T):
+        o_obs, o_rew, o_term, o_trunc = ora.step(acts[t])
+        assert relerr(obs[t], o_obs) < OBS_TOL and relerr(rew[t], o_rew) < OBS_TOL, t
+        clear = ~_borderline(ora)
+        assert np.array_equal(te[t], o_term) and np.array_equal(tr[t][clear], o_trunc[clear]), t
+    st = state_of(env)
+    assert relerr(st["pos"], ora.pos) < TIGHT and quat_err(st["quat"], ora.quat) < TIGHT
+    assert relerr(st["vel"], ora.vel) < TIGHT and relerr(st["rpy_rates"], ora.rpy_rates) < TIGHT

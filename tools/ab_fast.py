@@ -62,8 +62,8 @@ if __name__ == "__main__":
     if "--one" in sys.argv:
         one()
     else:
-        for env in ({"QS_PREFETCH": "0", "QS_EARLY_STORE": "0"}, {"QS_PREFETCH": "1", "QS_EARLY_STORE": "0"}, {"QS_PREFETCH": "0", "QS_EARLY_STORE": "1"},
-                    {"QS_PREFETCH": "1", "QS_EARLY_STORE": "1"}, {"QS_PREFETCH": "1", "QS_EARLY_STORE": "1", "QS_FAST_WARPS": "4"}):
+        for env in ({"QS_PREFETCH": "1", "QS_ROW_LOADS": "0"}, {"QS_PREFETCH": "2", "QS_ROW_LOADS": "0"}, {"QS_PREFETCH": "1", "QS_ROW_LOADS": "1"},
+                    {"QS_PREFETCH": "2", "QS_ROW_LOADS": "1"}, {"QS_PREFETCH": "2", "QS_ROW_LOADS": "1", "QS_EARLY_STORE": "0"}):
             e = dict(os.environ)
             e.update(env)
             subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=e, check=False)
