@@ -84,6 +84,32 @@ class DSLPIDControl(BaseControl):
             t = t.contiguous()
         return t, t.stride(0)
 
+    def computeControlFromEnv(self, env, target_pos, target_rpy=None, target_vel=None, target_rpy_rates=None, control_timestep=None):
+        """computeControl for every drone of `env` (num_drones == env's drone count), reading pos / quat / vel from the env's
+        float64 state on the device (qs_pid_control_state) and returning float64 RPMs [n, 4] in the env's float64
+        command buffer: `env.step(rpm)` with that tensor applies them without a copy or a float32 rounding
+        -- the pid.py loop (examples/pid.py:131-150) in float64 end to end.  Targets: [n, 3] arrays / tensors (float64)."""
+        n = env._N
+        if n != self.num_drones:
+            raise ValueError("controller for %d drones used with an env of %d" % (self.num_drones, n))
+        self.control_counter += 1
+        dev = self.device
+
+        def t64(x):
+            if x is None:
+                return None
+            t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float64))
+            return t.to(device=dev, dtype=torch.float64).reshape(n, 3).contiguous()
+        tp, tr, tv, trr = t64(target_pos), t64(target_rpy), t64(target_vel), t64(target_rpy_rates)
+        ptr = lambda t: None if t is None else t.data_ptr()      # noqa: E731
+        dt = float(env.CTRL_TIMESTEP if control_timestep is None else control_timestep)
+        with torch.cuda.device(dev):
+            rc = self._lib.qs_pid_control_state(C.byref(self._P), self._state.data_ptr(), dt, C.byref(env._st), n,
+                                                ptr(tp), ptr(tr), ptr(tv), ptr(trr), env._rpm_cmd.data_ptr(),
+                                                self._pos_e.data_ptr(), self._yaw_e.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        N.check(rc, "qs_pid_control_state")
+        return env._rpm_cmd.view(env._E, env._D, 4) if env.VECTORIZED else env._rpm_cmd
+
     def computeControl(self, control_timestep, cur_pos, cur_quat, cur_vel, cur_ang_vel, target_pos,
                        target_rpy=None, target_vel=None, target_rpy_rates=None):
         """Computes the PID control action (as RPMs) (DSLPIDControl.py:82-145).  `cur_ang_vel` is unused (:96)."""

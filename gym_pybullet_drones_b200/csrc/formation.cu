@@ -309,10 +309,12 @@ __global__ void __launch_bounds__(128) dw_publish_kernel(const __grid_constant__
 
 // ---------------------------------------------------------------------------------------------------------
 // Neighbourhood query (BaseAviary._getAdjacencyMatrix, BaseAviary.py:658-675): out[e][i][j] = (i == j) or
-// |pos_i - pos_j| < radius.  HBM-write bound (D^2 bytes per aviary): a thread produces 16 columns of one row as one
-// 16-byte store, a warp 512 contiguous bytes; the 512 column positions of a CTA sit in shared memory.  The
-// comparison is made in float32 and re-evaluated in float64 (sqrt(dx^2+dy^2+dz^2) < radius, the reference's
-// arithmetic) only when the float32 value is within 2e-4 relative of the threshold (warp-uniform rare branch).
+// |pos_i - pos_j| < radius.  HBM-write bound by nature (D^2 bytes per aviary), instruction-issue bound in practice
+// (>= 8 instructions per pair: 3 subtractions, 3 multiply-adds, compare, pack), so the work per pair is kept minimal:
+// a lane keeps the positions of its 16 consecutive COLUMNS in registers for the whole row tile (256 rows), the row
+// position is a warp-uniform load, the 16 results are packed into one 16-byte store (a warp writes 512 contiguous bytes
+// of a row).  The comparison is float32; pairs within 2e-4 (relative) of the threshold are re-evaluated with the
+// reference's float64 arithmetic on the float64 positions (rare, warp-voted branch).
 // ---------------------------------------------------------------------------------------------------------
 struct AdjArgs {
     const double* planes;
@@ -321,21 +323,30 @@ struct AdjArgs {
     int D, col_tiles, row_tiles;
 };
 
-constexpr int kAdjCols = 512, kAdjRows = 64;
+constexpr int kAdjCols = 512, kAdjRows = 256;
 
 __global__ void __launch_bounds__(256) adjacency_kernel(const __grid_constant__ AdjArgs a) {
-    __shared__ float4 cols[kAdjCols];
+    __shared__ float4 rows_s[kAdjRows];
     int b = blockIdx.x;
     const int ct = b % a.col_tiles; b /= a.col_tiles;
     const int rt = b % a.row_tiles;
     const int env = b / a.row_tiles;
     const long long base = (long long)env * a.D;
     const int c0 = ct * kAdjCols, r0 = rt * kAdjRows;
-    for (int k = threadIdx.x; k < kAdjCols; k += blockDim.x)
-        if (c0 + k < a.D) { const D4 v = ld256(a.planes, base + c0 + k); cols[k] = make_float4((float)v.x, (float)v.y, (float)v.z, 0.f); }
-        else cols[k] = make_float4(3e30f, 3e30f, 3e30f, 0.f);
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < kAdjRows; k += blockDim.x) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + k < a.D) { const D4 p = ld256(a.planes, base + r0 + k); v = make_float4((float)p.x, (float)p.y, (float)p.z, 0.f); }
+        rows_s[k] = v;
+    }
+    const int j0 = c0 + 16 * lane;                         // my 16 columns
+    float cx[16], cy[16], cz[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        if (j0 + q < a.D) { const D4 p = ld256(a.planes, base + j0 + q); cx[q] = (float)p.x; cy[q] = (float)p.y; cz[q] = (float)p.z; }
+        else { cx[q] = 3e30f; cy[q] = 3e30f; cz[q] = 3e30f; }
+    }
+    __syncthreads();
     const float r2f = (float)(a.radius * a.radius);
     float r2lo = r2f * (1.f - 2e-4f), r2hi = r2f * (1.f + 2e-4f);           // outside [lo, hi] float32 decides
     if (a.radius < 0.0) r2lo = r2hi = -1.f;                                 // |d| < negative radius: never
@@ -343,40 +354,41 @@ __global__ void __launch_bounds__(256) adjacency_kernel(const __grid_constant__ 
     for (int rr = warp; rr < kAdjRows; rr += 8) {
         const int i = r0 + rr;
         if (i >= a.D) break;
-        const D4 me_d = ld256(a.planes, base + i);
-        const float4 me = make_float4((float)me_d.x, (float)me_d.y, (float)me_d.z, 0.f);
-        // group q: lane evaluates column c0 + 32 q + lane (conflict-free LDS.128), the ballot collects the 32 results;
-        // lane q keeps the word, so lane L finds its 16 output columns in lane L/2's word, half L%2
-        unsigned word = 0u;
+        const float4 me = rows_s[rr];                                       // warp-uniform (broadcast)
+        unsigned w[4] = {0u, 0u, 0u, 0u};
+        unsigned amb = 0u;                                                  // bit q: pair q is within 2e-4 of the threshold
 #pragma unroll
-        for (int q = 0; q < kAdjCols / 32; ++q) {
-            const float4 o = cols[q * 32 + lane];
-            const float dx = o.x - me.x, dy = o.y - me.y, dz = o.z - me.z;
-            const float d2 = dx * dx + dy * dy + dz * dz;
-            bool near = d2 < r2lo;
-            const bool amb = !near && !(d2 > r2hi);
-            if (__any_sync(0xffffffffu, amb)) {                          // rare: within 2e-4 of the threshold -> reference arithmetic
-                if (amb) {                                                // the reference's float64 arithmetic on the float64 positions
-                    const D4 od = ld256(a.planes, base + c0 + q * 32 + lane);
-                    const double ex = me_d.x - od.x, ey = me_d.y - od.y, ez = me_d.z - od.z;
-                    near = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez))) < a.radius;
+        for (int q = 0; q < 16; ++q) {
+            const float dx = cx[q] - me.x, dy = cy[q] - me.y, dz = cz[q] - me.z;
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const bool near = d2 < r2lo;
+            amb |= (!near && !(d2 > r2hi)) ? (1u << q) : 0u;
+            w[q >> 2] |= near ? (1u << (8 * (q & 3))) : 0u;
+        }
+        if (__any_sync(0xffffffffu, amb != 0u)) {                           // rare: the reference's float64 arithmetic decides
+            if (amb) {
+                const D4 md = ld256(a.planes, base + i);
+                for (unsigned m = amb; m; m &= m - 1) {
+                    const int q = __ffs(m) - 1;
+                    if (j0 + q >= a.D) continue;
+                    const D4 od = ld256(a.planes, base + j0 + q);          // BaseAviary.py:670
+                    const double ex = md.x - od.x, ey = md.y - od.y, ez = md.z - od.z;
+                    const bool near = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez))) < a.radius;
+                    const unsigned bit = near ? (1u << (8 * (q & 3))) : 0u;
+                    if ((q >> 2) == 0) w[0] |= bit; else if ((q >> 2) == 1) w[1] |= bit; else if ((q >> 2) == 2) w[2] |= bit; else w[3] |= bit;
                 }
             }
-            const unsigned bits = __ballot_sync(0xffffffffu, near);
-            if (lane == q) word = bits;
         }
-        const int ci = i - c0;                                            // identity (BaseAviary.py:666)
-        if (ci >= 0 && ci < kAdjCols && lane == (ci >> 5)) word |= 1u << (ci & 31);
-        const unsigned h = (__shfl_sync(0xffffffffu, word, lane >> 1) >> ((lane & 1) * 16)) & 0xffffu;
-        unsigned w[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) w[k] = (((h >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u;
-        const int j = c0 + lane * 16;
-        unsigned char* dst = a.out + ((size_t)(base + i)) * a.D + j;
+        const int dj = i - j0;                                              // identity (BaseAviary.py:666)
+        if ((unsigned)dj < 16u) {
+            const unsigned bit = 1u << (8 * (dj & 3));
+            if ((dj >> 2) == 0) w[0] |= bit; else if ((dj >> 2) == 1) w[1] |= bit; else if ((dj >> 2) == 2) w[2] |= bit; else w[3] |= bit;
+        }
+        unsigned char* dst = a.out + ((size_t)(base + i)) * a.D + j0;
         if (vec) {
-            if (j < a.D) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (j0 < a.D) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
         } else {
-            for (int q = 0; q < 16 && j + q < a.D; ++q) dst[q] = (unsigned char)((w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+            for (int q = 0; q < 16 && j0 + q < a.D; ++q) dst[q] = (unsigned char)((w[q >> 2] >> (8 * (q & 3))) & 0xffu);
         }
     }
 }

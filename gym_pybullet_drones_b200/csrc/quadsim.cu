@@ -29,6 +29,39 @@ struct PidArgs {
     float *rpm_out, *pos_e_out, *yaw_e_out;
 };
 
+// pos / quat / vel from the float64 state planes, float64 targets, float64 RPMs out (qs_pid_control_state)
+struct PidStateArgs {
+    QsParams P;
+    double* pid;
+    double dt;
+    const double* planes;
+    const double *tpos, *trpy, *tvel, *trr;
+    long long n;
+    double* rpm_out;
+    float *pos_e_out, *yaw_e_out;
+};
+
+__global__ void __launch_bounds__(128) pid_state_kernel(const __grid_constant__ PidStateArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long N = a.n;
+    if (i >= N) return;
+    const D4 p0 = ld256(a.planes, i), p1 = ld256(a.planes, N + i), p2 = ld256(a.planes, 2 * N + i);
+    qs::PidState st;
+    load_pid(a.pid, N, i, st);
+    const double tyaw = a.trpy ? a.trpy[3 * i + 2] : 0.0;
+    double tv[3] = {0, 0, 0}, tr[3] = {0, 0, 0};
+    if (a.tvel) { tv[0] = a.tvel[3 * i]; tv[1] = a.tvel[3 * i + 1]; tv[2] = a.tvel[3 * i + 2]; }
+    if (a.trr) { tr[0] = a.trr[3 * i]; tr[1] = a.trr[3 * i + 1]; tr[2] = a.trr[3 * i + 2]; }
+    double rpm[4], pe[3], ye;
+    qs::pid_control(a.P, st, a.dt, p0.x, p0.y, p0.z, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z,
+                    a.tpos[3 * i], a.tpos[3 * i + 1], a.tpos[3 * i + 2], tyaw, tv[0], tv[1], tv[2], tr[0], tr[1], tr[2], rpm, pe, ye);
+    store_pid(a.pid, N, i, st);
+    st256(a.rpm_out, i, qs::clampd(rpm[0], 0.0, a.P.max_rpm), qs::clampd(rpm[1], 0.0, a.P.max_rpm),
+          qs::clampd(rpm[2], 0.0, a.P.max_rpm), qs::clampd(rpm[3], 0.0, a.P.max_rpm));            // CtrlAviary.py:140
+    if (a.pos_e_out) { a.pos_e_out[3 * i] = (float)pe[0]; a.pos_e_out[3 * i + 1] = (float)pe[1]; a.pos_e_out[3 * i + 2] = (float)pe[2]; }
+    if (a.yaw_e_out) a.yaw_e_out[i] = (float)ye;
+}
+
 __global__ void __launch_bounds__(128) pid_kernel(const __grid_constant__ PidArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long N = a.n;
@@ -413,6 +446,7 @@ int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, floa
     if (int rc = check_state(st, 0)) return rc;
     if (n_envs <= 0 || drones_per_env <= 0 || substeps <= 0) return fail(QS_ERR_SIZE, "qs_dyn_substeps: sizes must be > 0");
     if (rpm && !aligned16(rpm)) return fail(QS_ERR_ALIGN, "qs_dyn_substeps: rpm must be 16-byte aligned");
+    if (rpm && (flags & QS_FLAG_ACTION_F64) && !aligned32(rpm)) return fail(QS_ERR_ALIGN, "qs_dyn_substeps: float64 rpm must be 32-byte aligned");
     if (effects & ~7u) return fail(QS_ERR_ENUM, "qs_dyn_substeps: bad effects");
     if ((effects & QS_EFFECT_DRAG) && !st->last_rpm) return fail(QS_ERR_NULL, "qs_dyn_substeps: DRAG needs QsState.last_rpm");
     if ((effects & QS_EFFECT_DW) && !dw_fz && drones_per_env > kMaxTPB)
@@ -428,7 +462,7 @@ int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, floa
     a.cap = cta_capacity(a.N, drones_per_env);
     a.tpb = block_size_for(drones_per_env, a.cap);
     a.counter_inc = substeps;
-    a.effects = effects; a.flags = flags & (QS_FLAG_RPY_F32 | QS_FLAG_RPM_FROM_LAST);
+    a.effects = effects; a.flags = flags & (QS_FLAG_RPY_F32 | QS_FLAG_RPM_FROM_LAST | QS_FLAG_ACTION_F64);
     const cudaError_t e = launch_step_general(a, true, false, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_dyn_substeps launch");
 }
@@ -450,6 +484,22 @@ int qs_pid_control(const QsParams* p, double* pid_state, double control_timestep
     pid_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_pid_control launch");
+}
+
+int qs_pid_control_state(const QsParams* p, double* pid_state, double control_timestep, const QsState* st, int n,
+                         const double* target_pos, const double* target_rpy, const double* target_vel, const double* target_rpy_rates,
+                         double* rpm_out, float* pos_e_out, float* yaw_e_out, void* stream) {
+    if (!p || !pid_state || !st || !st->planes || !target_pos || !rpm_out) return fail(QS_ERR_NULL, "qs_pid_control_state: NULL argument");
+    if (n <= 0) return fail(QS_ERR_SIZE, "qs_pid_control_state: n must be > 0");
+    if (!(control_timestep > 0.0)) return fail(QS_ERR_SIZE, "qs_pid_control_state: control_timestep must be > 0");
+    if (!aligned32(st->planes) || !aligned32(rpm_out)) return fail(QS_ERR_ALIGN, "qs_pid_control_state: planes / rpm_out must be 32-byte aligned");
+    PidStateArgs a;
+    a.P = *p; a.pid = pid_state; a.dt = control_timestep; a.planes = st->planes;
+    a.tpos = target_pos; a.trpy = target_rpy; a.tvel = target_vel; a.trr = target_rpy_rates; a.n = n;
+    a.rpm_out = rpm_out; a.pos_e_out = pos_e_out; a.yaw_e_out = yaw_e_out;
+    pid_state_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "qs_pid_control_state launch");
 }
 
 int qs_wait_flags(const unsigned* flags, unsigned seq, int world, unsigned* err_flag, void* stream) {

@@ -132,6 +132,9 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
         load_drone(a.st.planes, N, i, d);
         if (a.io.action == nullptr) {
             // CtrlAviary split substeps: the rpm come from last_rpm (RPM_FROM_LAST)
+        } else if (RAW && (a.flags & QS_FLAG_ACTION_F64)) {
+            const D4 v = ld256(reinterpret_cast<const double*>(a.io.action), i);      // float64 RPMs
+            rpm[0] = v.x; rpm[1] = v.y; rpm[2] = v.z; rpm[3] = v.w;
         } else if (A == 4) {
             const float4 v = ldg4(a.io.action, i);
             act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
@@ -171,6 +174,9 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
         }
         if (a.flags & QS_FLAG_RPM_FROM_LAST) {
             rpm[0] = rpm_prev[0]; rpm[1] = rpm_prev[1]; rpm[2] = rpm_prev[2]; rpm[3] = rpm_prev[3];
+        } else if (RAW && (a.flags & QS_FLAG_ACTION_F64)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rpm[k] = qs::clampd(rpm[k], 0.0, P.max_rpm);              // CtrlAviary.py:140
         } else {
             qs::decode_action<PIDACT>(P, a.act_type, act, d, cur_yaw, pst, rpm);
         }

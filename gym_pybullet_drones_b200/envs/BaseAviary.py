@@ -282,6 +282,7 @@ class BaseAviary(Env):
         self._pos_f32 = torch.zeros((n, 4), **f32) if big_dw else None                       # float32 position mirror (pair kernels)
         self._dw_boxes = torch.zeros((E, (D + 31) // 32, 8), **f32) if big_dw else None     # chunk boxes (qs_downwash_boxed)
         self._action_dev = torch.zeros((n, self._A), **f32)
+        self._rpm_cmd = torch.zeros((n, 4), **f64) if raw and self._act_type() == N.ACT_RAW_RPM else None      # float64 RPM commands
         #### tables ####
         if np.asarray(self.INIT_XYZS).ndim != np.asarray(self.INIT_RPYS).ndim and self._tables_per_env:
             pass  # _table() broadcasts the [D,3] one
@@ -489,10 +490,11 @@ class BaseAviary(Env):
 
     ################################################################################
 
-    def _launch(self, action_dev):
+    def _launch(self, action_dev, f64=False):
         """One control tick on the device (BaseAviary.step, BaseAviary.py:259-383)."""
         io, cur = self._io, self._cur
         io.action = action_dev.data_ptr()
+        f64_flag = N.FLAG_ACTION_F64 if f64 else 0
         io.obs_prev = self._obs_buf[cur].data_ptr()
         io.obs = self._obs_buf[1 - cur].data_ptr()
         S = self.PYB_STEPS_PER_CTRL
@@ -504,7 +506,7 @@ class BaseAviary(Env):
         if self._dw_fz is None:
             if raw:
                 rc = L.qs_dyn_substeps(C.byref(self._P), C.byref(self._st), io.action, io.obs, None,
-                                       self._E, self._D, S, self._effects, self._flags, stream)
+                                       self._E, self._D, S, self._effects, self._flags | f64_flag, stream)
             else:
                 rc = L.qs_step(C.byref(self._P), C.byref(self._st), C.byref(io), self._act_type(), self._task(),
                                self._E, self._D, S, self._effects, self._flags, stream)
@@ -515,7 +517,7 @@ class BaseAviary(Env):
                 self._downwash_stage(stream)
                 if raw:
                     last = s == S - 1
-                    fl = self._flags | (N.FLAG_RPM_FROM_LAST if s > 0 else 0)      # substeps 1.. re-read the clipped rpm of substep 0
+                    fl = self._flags | (N.FLAG_RPM_FROM_LAST if s > 0 else f64_flag)      # substeps 1.. re-read the clipped rpm of substep 0
                     rc = L.qs_dyn_substeps(C.byref(self._P), C.byref(self._st), io.action if s == 0 else None, io.obs if last else None,
                                            self._dw_fz.data_ptr(), self._E, self._D, 1, self._effects, fl, stream)
                 else:
@@ -584,6 +586,14 @@ class BaseAviary(Env):
             return (self._obs_view[cur], self._reward, self._terminated, self._truncated,
                     {"final_obs": self._final_view, "_final_obs": self._done})
         with self._on_device():
+            if isinstance(action, torch.Tensor) and action.dtype == torch.float64 and self._act_type() == N.ACT_RAW_RPM:
+                #### float64 RPMs (e.g. DSLPIDControl.computeControlFromEnv): no float32 rounding on the way in ####
+                if action.data_ptr() != self._rpm_cmd.data_ptr():
+                    self._rpm_cmd.copy_(action.to(self.device).reshape(self._N, 4))
+                obs = self._launch(self._rpm_cmd, f64=True)
+                if not self.VECTORIZED:
+                    return self._single_result(obs)
+                return self._shape_obs(obs), self._reward, self._terminated, self._truncated, {}
             if isinstance(action, torch.Tensor):
                 a = action
                 if a.device != self.device or a.dtype != torch.float32:
@@ -600,6 +610,10 @@ class BaseAviary(Env):
                     info = {"final_obs": self._final_obs.view(self._E, self._D, self._obs_dim), "_final_obs": self._done}
                 return self._shape_obs(obs), self._reward, self._terminated, self._truncated, info
             #### NumPy path: pinned H2D of the action, D2H of the results, all inside this call ####
+            if self._rpm_cmd is not None and isinstance(action, np.ndarray) and action.dtype == np.float64:
+                # CtrlAviary with the reference's float64 RPM arrays (examples/pid.py:143): no float32 rounding on the way in
+                self._rpm_cmd.copy_(torch.from_numpy(np.ascontiguousarray(action).reshape(self._N, 4)))
+                return self.step(self._rpm_cmd)
             a_np = np.asarray(action, dtype=np.float32).reshape(self._N, self._A)
             if self._simple_launch:
                 o, rew, term, trunc, info = self._step_host(a_np)

@@ -71,7 +71,9 @@ enum { QS_FLAG_AUTORESET_SAME_STEP = 1,   /* SB3 VecEnv semantics: done envs are
           all but the last launch of a tick pass SKIP_EPILOGUE (no obs/reward/flags/counter); all but the first
           pass RPM_FROM_LAST (the rpm decoded by the first launch is re-read from QsState.last_rpm). */
        QS_FLAG_SKIP_EPILOGUE = 0x100,
-       QS_FLAG_RPM_FROM_LAST = 0x200 };
+       QS_FLAG_RPM_FROM_LAST = 0x200,
+       QS_FLAG_ACTION_F64 = 0x400 };      /* qs_dyn_substeps: `rpm` points to float64 [N][4] (32-byte aligned), e.g. the output of
+                                             qs_pid_control_state: the reference's float64 RPMs without a float32 rounding */
 
 enum { QS_ERR_NULL = -1, QS_ERR_ALIGN = -2, QS_ERR_SIZE = -3, QS_ERR_ENUM = -4, QS_ERR_UNSUPPORTED = -5 };
 
@@ -288,6 +290,16 @@ int qs_pid_control(const QsParams* p, double* pid_state, double control_timestep
                    const float* cur_vel, int vel_stride,
                    const float* target_pos, const float* target_rpy, const float* target_vel, const float* target_rpy_rates,
                    int n, float* rpm_out, float* pos_e_out, float* yaw_e_out, void* stream);
+
+/* The same controller for the n = n_envs * drones_per_env drones of a simulator state: pos / quat / vel are read from the
+ * float64 planes (three coalesced 32-byte accesses per drone instead of strided float32 state vectors), the targets are
+ * float64 [n][3] (target_rpy / target_vel / target_rpy_rates nullable = zeros), and the RPMs are written as float64 [n][4],
+ * clipped to [0, MAX_RPM] like CtrlAviary._preprocessAction (envs/CtrlAviary.py:121-140) -- e.g. straight into
+ * QsState.last_rpm, from where qs_dyn_substeps(QS_FLAG_RPM_FROM_LAST, rpm = NULL) applies them: the pid.py control loop
+ * (examples/pid.py:131-150) in float64 end to end, with nothing leaving the device. */
+int qs_pid_control_state(const QsParams* p, double* pid_state, double control_timestep, const QsState* st, int n,
+                         const double* target_pos, const double* target_rpy, const double* target_vel, const double* target_rpy_rates,
+                         double* rpm_out, float* pos_e_out, float* yaw_e_out, void* stream);
 
 /* Pairwise downwash within each aviary: fz_out[n] = sum over drones i of the same aviary with dz>0, dxy<10 of
  * -alpha*exp(-.5 (dxy/beta)^2) (force along n's body z).  Reads the float32 position mirror QsState.pos_f32. */

@@ -196,9 +196,9 @@ def test_rl_pid_trajectory_120hz(golden, key, nd, act):
 
 
 def test_pid_circle_workload(golden):
-    """examples/pid.py: CtrlAviary(DYN, 240/48) x 3 + DSLPIDControl through computeControlFromState; free-running for 8
-    ticks, then teacher-forced (the 48 Hz loop amplifies rounding ~1.5x per tick in the reference itself, so float32
-    I/O noise of 1e-7 reaches 1e-4 within ~17 ticks)."""
+    """examples/pid.py: CtrlAviary(DYN, 240/48) x 3 + DSLPIDControl; free-running for 8 ticks, then teacher-forced (the
+    48 Hz loop amplifies any perturbation ~1.5x per tick in the reference itself).  The controller reads the env's float64
+    state on the device (computeControlFromEnv) and the env takes its float64 RPMs: no float32 rounding in the loop."""
     DSLPIDControl, CtrlAviary, _, _, _, DroneModel, Physics, _ = _imports()
     g = golden("pid_circle_cf2x")
     env = CtrlAviary(num_drones=3, initial_xyzs=g["INIT_XYZS"], initial_rpys=g["INIT_RPYS"], physics=Physics.DYN, pyb_freq=240, ctrl_freq=48)
@@ -213,13 +213,13 @@ def test_pid_circle_workload(golden):
             action = g["action"][t - 1]
         obs, _, _, _, _ = env.step(action)
         ref = g["obs"][t]
-        # free-running ticks: the 48 Hz loop multiplies any perturbation by ~1.5 per tick IN THE REFERENCE, and the float32
-        # RPM / state-vector interface between CtrlAviary and the controller injects 6e-8 every tick
-        tol = 5e-5 if t <= 8 else RTOL
+        tol = RTOL              # (the observation is float32; the float64 state is checked through the next tick's RPMs)
         assert relerr(obs[:, 0:3], ref[:, 0:3]) < tol and quat_err(obs[:, 3:7], ref[:, 3:7]) < tol and relerr(obs[:, 7:16], ref[:, 7:16]) < tol, t
-        rpm, pe, ye = ctrl.computeControlFromState(env.CTRL_TIMESTEP, obs, g["target"][t], target_rpy=g["INIT_RPYS"])
+        rpm = ctrl.computeControlFromEnv(env, g["target"][t], target_rpy=g["INIT_RPYS"])
         if t > 8:
-            assert relerr(rpm, g["action"][t]) < 1e-4, t
+            assert relerr(rpm.cpu().numpy(), g["action"][t]) < 1e-7, t
+        elif t > 0:
+            assert relerr(rpm.cpu().numpy(), g["action"][t]) < 1e-6, t          # free-running: 1e-12 x 1.5^t x the D-gain
         action = rpm
 
 

@@ -1,4 +1,4 @@
-"""Throughput of the other BASELINE.json configs (not the headline bench line): writes gpurun_out/configs_r01.json.
+"""Throughput of the other BASELINE.json configs (not the headline bench line): writes gpurun_out/configs_r02.json.
     config 2: 4096 x HoverAviary with the embedded DSLPIDControl (act=PID), + stand-alone qs_pid_control
     config 3b: learn.py's ONE_D_RPM variant of the headline workload (A=1, obs 27)
     config 4: one 16384-drone formation with ground effect + downwash (pairwise kernel + one launch per substep)
@@ -55,6 +55,15 @@ for n in (4096, 1048576):
     tp = torch.rand((n, 3), device=dev, generator=g)
     ms = timed(lambda: ctrl.computeControl(1 / 48, pos, q, vel, None, tp), 200, 10)
     out["qs_pid_control_%d" % n] = {"n": n, "ms_per_call": ms, "calls_per_s": n / (ms * 1e-3), "alg_bytes": 192, "hbm_frac": 192 * n / (ms * 1e-3) / 1e9 / PEAK}
+    # the same controller reading the float64 state planes of an env (qs_pid_control_state): coalesced 32-byte loads, float64 RPMs out
+    cenv = CtrlAviary(num_drones=1, physics=Physics.DYN, num_envs=n)
+    cenv.reset()
+    tp64 = tp.double()
+    ms = timed(lambda: ctrl.computeControlFromEnv(cenv, tp64, control_timestep=1 / 48), 200, 10)
+    actual = 96 + 72 + 72 + 24 + 32 + 16          # planes r, pid state r/w (float64), target r, rpm w (float64), pos_e/yaw_e w
+    out["qs_pid_control_state_%d" % n] = {"n": n, "ms_per_call": ms, "calls_per_s": n / (ms * 1e-3), "alg_bytes": 192, "actual_bytes": actual,
+                                          "hbm_frac": 192 * n / (ms * 1e-3) / 1e9 / PEAK, "hbm_frac_actual_bytes": actual * n / (ms * 1e-3) / 1e9 / PEAK}
+    del cenv
 
 # config 3b: ONE_D_RPM
 E, D = 32768, 2
@@ -162,5 +171,5 @@ env_b.reset()
 ms_b = dw_ms(env_b, True)
 out["formation_65536_downwash_culled_morton"] = {"drones": Db, "S": 1, "ms_per_step": ms_b, "drone_steps_per_s": Db / (ms_b * 1e-3),
                                                   "pairs_per_s": Db * Db / (ms_b * 1e-3), "note": "downwash kernel only; 4.3e9 pairs, culled"}
-json.dump(out, open("gpurun_out/configs_r01.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/configs_r02.json", "w"), indent=1)
 print(json.dumps(out, indent=1))
