@@ -683,10 +683,15 @@ class BaseAviary(Env):
         with self._on_device():
             if self._hook_pre:                                 # raw-RPM envs: action -> RPMs (CtrlAviary.py:121-140)
                 action = self._preprocessAction(action)
-            a = action if isinstance(action, torch.Tensor) else torch.as_tensor(np.asarray(action, dtype=np.float32))
-            a = a.to(device=self.device, dtype=torch.float32).reshape(self._N, self._A)
-            self._action_dev.copy_(a)
-            self._launch(self._action_dev)
+            f64 = self._rpm_cmd is not None and getattr(action, "dtype", None) in (np.float64, torch.float64)
+            if f64:                                            # raw-RPM envs keep the reference's float64 RPMs
+                a = action if isinstance(action, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(action))
+                self._rpm_cmd.copy_(a.to(self.device).reshape(self._N, 4))
+                self._launch(self._rpm_cmd, f64=True)
+            else:
+                a = action if isinstance(action, torch.Tensor) else torch.as_tensor(np.asarray(action, dtype=np.float32))
+                self._action_dev.copy_(a.to(device=self.device, dtype=torch.float32).reshape(self._N, self._A))
+                self._launch(self._action_dev)
             obs = self._computeObs()
             rew, term, trunc = self._computeReward(), self._computeTerminated(), self._computeTruncated()
             if not self.VECTORIZED:

@@ -23,7 +23,7 @@ def one():
     out = {}
     scrub = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for act, A in (("RPM", 4), ("ONE_D_RPM", 1)):
-        for n in (65536, 1048576):
+        for n in ((65536,) if os.environ.get("QS_AB_SMALL") else (65536, 1048576)):
             R = 8 if n == 65536 else 2
             envs = [MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType[act], num_envs=n // D, autoreset="same_step") for _ in range(R)]
             acts = [torch.rand((n // D, D, A), device=dev, generator=g) * 2 - 1 for _ in envs]
@@ -62,8 +62,8 @@ if __name__ == "__main__":
     if "--one" in sys.argv:
         one()
     else:
-        for env in ({"QS_PREFETCH": "1", "QS_ROW_LOADS": "0"}, {"QS_PREFETCH": "2", "QS_ROW_LOADS": "0"}, {"QS_PREFETCH": "1", "QS_ROW_LOADS": "1"},
-                    {"QS_PREFETCH": "2", "QS_ROW_LOADS": "1"}, {"QS_PREFETCH": "2", "QS_ROW_LOADS": "1", "QS_EARLY_STORE": "0"}):
+        for env in ({"QS_STAGGER_NS": "0"}, {"QS_STAGGER_NS": "1000", "QS_STAGGER_MODE": "0"}, {"QS_STAGGER_NS": "1500", "QS_STAGGER_MODE": "0"},
+                    {"QS_STAGGER_NS": "1500", "QS_STAGGER_MODE": "1"}, {"QS_STAGGER_NS": "2500", "QS_STAGGER_MODE": "1"}, {"QS_STAGGER_NS": "1500", "QS_STAGGER_MODE": "2"}):
             e = dict(os.environ)
             e.update(env)
             subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=e, check=False)
