@@ -64,6 +64,7 @@ class QsStepIO(C.Structure):
         ("act_buffer_size", C.c_int), ("tick_substeps", C.c_int),
         ("obs_gather", C.c_void_p), ("reward_gather", C.c_void_p), ("terminated_gather", C.c_void_p), ("truncated_gather", C.c_void_p),
         ("gather_flag", C.c_void_p), ("gather_counter", C.c_void_p), ("gather_seq", C.c_uint), ("pad_", C.c_uint),
+        ("pdl_hint", C.c_void_p),
     ]
 
 

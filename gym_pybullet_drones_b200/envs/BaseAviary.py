@@ -320,6 +320,8 @@ class BaseAviary(Env):
         io.dw_fz = self._dw_fz.data_ptr() if self._dw_fz is not None else None
         io.act_buffer_size = self._B
         io.tick_substeps = 0
+        self._pdl_hint = torch.zeros((1,), dtype=torch.int32, device=dev)
+        io.pdl_hint = self._pdl_hint.data_ptr()
         self._io = io
         #### pre-resolved handles for the per-step fast path ####
         self._obs_ptr = [b.data_ptr() for b in self._obs_buf]

@@ -171,6 +171,11 @@ typedef struct QsStepIO {
     unsigned* gather_counter;           /* one zeroed device word owned by the caller (arrival count); required with gather_flag */
     unsigned gather_seq;
     unsigned pad_;
+    unsigned* pdl_hint;                 /* optional device word owned by the caller (one per env, zero-initialised): the kernel records in it
+                                           whether its launch found a programmatic-dependent-launch window (it was resident while its
+                                           predecessor still ran); the next launch on the same buffers then prefetches its observation
+                                           history into L2 during that window, and an isolated launch does not (the prefetch would only
+                                           delay its state loads).  NULL = always prefetch. */
 } QsStepIO;
 
 /* Spins (bounded, ~2 s, then *err_flag = 1) until flags[r] - seq >= 0 for every r < world: the learner side of obs_gather. */
