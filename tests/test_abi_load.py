@@ -99,3 +99,37 @@ def test_product_package_does_not_import_the_oracle():
                 src = open(os.path.join(base, f)).read()
                 assert "oracle" not in src.replace("oracle/", "").replace("the oracle", "") or "import oracle" not in src and "from oracle" not in src, f
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_round2_entry_points_validate_arguments_without_a_gpu():
+    """qs_pid_control_state / qs_log_append / qs_wait_flags / qs_reset_heads / the policy of qs_rollout / obs_gather of qs_step:
+    argument errors come back as negative codes with a message, nothing is launched."""
+    lib = N.lib()
+    P, st = N.QsParams(), N.QsState()
+    assert lib.qs_pid_control_state(C.byref(P), None, 0.02, C.byref(st), 4, None, None, None, None, None, None, None, None) == -1
+    assert lib.qs_wait_flags(None, 1, 2, None, None) == -1 and b"flags" in lib.qs_last_error()
+    buf = (C.c_char * 4096)()
+    base = (C.addressof(buf) + 63) & ~63
+    assert lib.qs_wait_flags(base, 1, 99, None, None) == -3
+    assert lib.qs_reset_heads(C.byref(st), 4, 0, None, None) == -1
+    ring = N.QsLogRing()
+    assert lib.qs_log_append(C.byref(P), C.byref(st), base, 20, None, C.byref(ring), 1, 4, None) == -1
+    assert lib.qs_sizeof_log_ring() == C.sizeof(N.QsLogRing)
+    assert lib.qs_host_is_pinned(None) == 0
+    # obs_gather needs a configuration of the fast kernels and 16-byte alignment
+    io = N.QsStepIO()
+    st.planes, st.step_counter = base, base + 2048
+    st.target_pos = base + 1024
+    io.action, io.obs_prev, io.obs = base + 256, base + 512, base + 768
+    io.reward, io.terminated, io.truncated = base + 1280, base + 1536, base + 1600
+    io.act_buffer_size = 15
+    io.obs_gather = base + 3000 + 4                                    # misaligned
+    assert lib.qs_step(C.byref(P), C.byref(st), C.byref(io), 0, 1, 4, 1, 8, 0, 0, None) == -2
+    io.obs_gather = base + 3008
+    assert lib.qs_step(C.byref(P), C.byref(st), C.byref(io), 1, 1, 4, 1, 8, 0, 0, None) in (-1, -5)   # PID action: not a fast-kernel configuration
+    # the on-device policy: RPM / ONE_D_RPM only, complete actor, matching widths
+    rio, pol = N.QsRolloutIO(), N.QsPolicy()
+    rio.obs_init, rio.obs, rio.reward, rio.terminated, rio.truncated = base + 512, base + 768, base + 1280, base + 1536, base + 1600
+    rio.T, rio.act_buffer_size = 4, 15
+    rio.policy = C.addressof(pol)
+    assert lib.qs_rollout(C.byref(P), C.byref(st), C.byref(rio), 0, 1, 4, 2, 8, 0, 0, None) == -1 and b"policy" in lib.qs_last_error()
