@@ -383,6 +383,27 @@ def main():
            "api": "MultiHoverAviary.step(page-locked ndarray) -> ndarrays (qs_step_host: H2D actions, tick, device-side compaction of the "
                   "finished aviaries, D2H obs/reward/flags + their terminal observations; host_copy=False)"}
     del hbuf
+    # the same loop with host_obs="head": only the 12-float kinematic head of every observation crosses PCIe (the rest of a KIN
+    # observation is the action history the caller supplied itself) -- reported next to the headline e2e, never instead of it
+    try:
+        henv = [MultiHoverAviary(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E, device=dev, autoreset="same_step",
+                                 host_copy=False, host_obs="head") for _ in range(2)]
+        for e in henv:
+            e.reset()
+        for k in range(4):
+            henv[k & 1].step(h_acts[k % R][k % K_ACT])
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            henv[k & 1].step(h_acts[k % R][(k // R) % K_ACT])
+        barrier()
+        hs = all_max(time.perf_counter() - t0)
+        e2e["head_only_mode"] = {"value": DRONES_PER_GPU * world * e2e_steps / hs, "ms_per_step": 1e3 * hs / e2e_steps,
+                                 "d2h_bytes_per_step_obs": DRONES_PER_GPU * 12 * 4,
+                                 "note": "extra: MultiHoverAviary(host_obs='head').step(ndarray) returns [E, D, 12] heads; terminal observations still travel in full"}
+        del henv
+    except Exception as ex:  # pragma: no cover
+        e2e["head_only_mode"] = {"error": repr(ex)}
 
     extras = {} if a.no_extras else run_extras(a, envs, acts, gen, dev, world, R, peak_gbs, barrier)
 

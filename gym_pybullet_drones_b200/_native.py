@@ -84,7 +84,7 @@ class QsPolicy(C.Structure):
 class QsHostIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("action_host", "obs_host", "reward_host", "terminated_host", "truncated_host", "done_host",
                                           "final_obs_host", "final_env_host", "n_final_host", "action_dev", "final_env_dev", "n_final_dev",
-                                          "side_stream", "ev_fork", "ev_join")]
+                                          "obs_head_host", "side_stream", "ev_fork", "ev_join")]
 
 
 class QsLogRing(C.Structure):

@@ -248,6 +248,16 @@ __global__ void __launch_bounds__(256) small_outputs_kernel(const float* __restr
     }
 }
 
+// kinematic heads of the observation rows -> packed [N][12] array (mapped host memory): head-only transfer mode of qs_step_host
+__global__ void __launch_bounds__(256) pack_heads_kernel(const float* __restrict__ obs, int od, long long N, float* __restrict__ dst) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 of a head per thread (rows are 16-byte multiples)
+    if (j >= 3 * N) return;
+    const long long r = j / 3;
+    const int c = (int)(j - 3 * r);
+    if ((od & 3) == 0) reinterpret_cast<float4*>(dst)[j] = *reinterpret_cast<const float4*>(obs + r * od + 4 * c);
+    else { const float* s = obs + r * od + 4 * c; float* d = dst + 4 * j; d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; }
+}
+
 // rows of the k finished aviaries (one aviary = D*obs_dim contiguous floats) -> compact array, indices and k alongside;
 // dst / idx_out / k_out may be mapped host memory (the stores then travel over PCIe next to the observation copy)
 __global__ void __launch_bounds__(128) gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, const int* __restrict__ count,
@@ -462,7 +472,14 @@ int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const
         cudaMemcpyAsync(h->truncated_host, io->truncated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
         if (io->done && h->done_host) cudaMemcpyAsync(h->done_host, io->done, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
     }
-    cudaMemcpyAsync(h->obs_host, io->obs, (size_t)N * od * 4, cudaMemcpyDeviceToHost, s);
+    if (h->obs_head_host && !state20) {
+        float* heads_h = nullptr;
+        if ((e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&heads_h), h->obs_head_host, 0)) != cudaSuccess)
+            return cuda_fail(e, "qs_step_host: obs_head_host must be pinned, mapped host memory");
+        pack_heads_kernel<<<(unsigned)((3 * N + 255) / 256), 256, 0, s>>>(io->obs, od, N, heads_h);
+    } else {
+        cudaMemcpyAsync(h->obs_host, io->obs, (size_t)N * od * 4, cudaMemcpyDeviceToHost, s);
+    }
     if (forked) cudaStreamWaitEvent(s, (cudaEvent_t)h->ev_join, 0);
     const double t1 = trace ? now() : 0.0;
     e = cudaStreamSynchronize(s);

@@ -240,6 +240,9 @@ typedef struct QsHostIO {
     float* action_dev;               /* caller-owned device scratch [N][A] */
     long long* final_env_dev;        /* caller-owned device scratch [E] */
     int* n_final_dev;                /* caller-owned device scratch [1] */
+    float* obs_head_host;            /* optional [N][12] (pinned, mapped): when set, only the kinematic head (pos3 rpy3 vel3 ang_v3) of every
+                                        observation row travels -- packed by a kernel into this array -- and obs_host is NOT written: a caller
+                                        that supplied the actions already holds the action-history part of the rows (5/6 of the bytes) */
     void* side_stream;               /* optional cudaStream_t for the compaction + gather of the terminal observations */
     void* ev_fork;                   /* optional cudaEvent_t pair (timing disabled) used to fork/join side_stream; both or neither */
     void* ev_join;

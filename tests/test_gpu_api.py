@@ -384,3 +384,27 @@ def test_rollout_with_on_device_policy_matches_torch_mlp(cls, act, D, critic):
     out = e2.rollout(policy=pol, num_steps=3)
     raw, logp, _ = pol.forward_torch(e1.reset()[0])
     assert float((out["actions"][0].reshape(E, -1) - raw).abs().max()) < 1e-5 and float((out["log_probs"][0] - logp).abs().max()) < 1e-4
+
+
+def test_numpy_api_head_only_transfer_mode():
+    """host_obs='head': the NumPy vector API moves only the kinematic head of every observation (the action-history part is
+    what the caller itself supplied); it equals the first 12 columns of the full observation, flags and terminal
+    observations are unchanged."""
+    from gym_pybullet_drones_b200.envs import MultiHoverAviary
+    from gym_pybullet_drones_b200.utils.enums import ActionType, Physics
+    E, D = 256, 2
+    kw = dict(num_drones=D, physics=Physics.DYN, act=ActionType.RPM, num_envs=E, autoreset="same_step")
+    e1, e2 = MultiHoverAviary(**kw), MultiHoverAviary(host_obs="head", **kw)
+    e1.reset(); e2.reset()
+    rng = np.random.default_rng(4)
+    seen = 0
+    for t in range(60):
+        a = rng.uniform(-1, 1, (E, D, 4)).astype(np.float32)
+        o1, r1, te1, tr1, i1 = e1.step(a)
+        o2, r2, te2, tr2, i2 = e2.step(a)
+        assert o2.shape == (E, D, 12) and np.array_equal(o2, o1[..., :12]) and np.array_equal(r1, r2)
+        assert np.array_equal(te1, te2) and np.array_equal(tr1, tr2)
+        if "final_obs" in i1:
+            seen += 1
+            assert np.array_equal(i1["final_obs"], i2["final_obs"]) and np.array_equal(i1["final_obs_env"], i2["final_obs_env"])
+    assert seen > 5

@@ -202,3 +202,31 @@ def test_p2p_needs_chunk_aligned_shards():
     _, _, FormationShard, _, Physics, _ = _imports()
     with pytest.raises(ValueError):
         FormationShard(stacks(5, 5), physics=Physics.PYB_DW, exchange="p2p", rank=0, world=2)
+
+
+def test_device_morton_resort_keeps_drone_ids_and_trajectories():
+    """reorder_by_morton(): a formation stored in a spatially incoherent order is re-binned on the device every few ticks;
+    actions and observations keep the caller's drone ids, the trajectories equal those of the untouched env up to the
+    float32 summation order of the pair term, and the culled downwash kernel gets cheaper."""
+    N, CtrlAviary, _, morton_order, Physics, O = _imports()
+    xyz = stacks(16, 16)                                                    # 1024 drones
+    rng = np.random.default_rng(3)
+    xyz = xyz[rng.permutation(len(xyz))]                                    # scrambled storage order
+    n, T = len(xyz), 12
+    kw = dict(num_drones=n, initial_xyzs=xyz, physics=Physics.PYB_GND_DRAG_DW, pyb_freq=240, ctrl_freq=48, num_envs=1)
+    a, b = CtrlAviary(**kw), CtrlAviary(**kw)
+    a.reset(); b.reset()
+    hover = O.OracleParams().HOVER_RPM
+    for t in range(T):
+        if t % 3 == 0:
+            order = b.reorder_by_morton()
+            assert sorted(order.cpu().tolist()) == list(range(n))
+        act = torch.from_numpy((hover * (1 + 0.05 * rng.uniform(-1, 1, (1, n, 4)))).astype(np.float32)).cuda()
+        oa, *_ = a.step(act)
+        ob, *_ = b.step(act)
+        assert relerr(ob[..., 0:3].cpu().numpy(), oa[..., 0:3].cpu().numpy()) < 1e-6 and relerr(ob[..., 10:13].cpu().numpy(), oa[..., 10:13].cpu().numpy()) < 1e-5, t
+    # storage order of b is now spatially coherent: its chunk boxes are small
+    def box_volume(env):
+        p = env._pos_f32[:, 0:3].view(-1, 32, 3)
+        return float(((p.max(dim=1).values - p.min(dim=1).values).clamp_min(1e-3)).prod(dim=1).mean())
+    assert box_volume(b) < 0.2 * box_volume(a)
