@@ -447,7 +447,8 @@ int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const
             forked = true;
             // the per-aviary outputs travel by kernel stores into the (mapped) host arrays on the side stream as well
             float* rew_h = nullptr; unsigned char *te_h = nullptr, *tr_h = nullptr, *dn_h = nullptr;
-            if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&rew_h), h->reward_host, 0) == cudaSuccess &&
+            static const bool small_kernel = !(getenv("QS_SMALL_OUT") && atoi(getenv("QS_SMALL_OUT")) == 0);
+            if (small_kernel && cudaHostGetDevicePointer(reinterpret_cast<void**>(&rew_h), h->reward_host, 0) == cudaSuccess &&
                 cudaHostGetDevicePointer(reinterpret_cast<void**>(&te_h), h->terminated_host, 0) == cudaSuccess &&
                 cudaHostGetDevicePointer(reinterpret_cast<void**>(&tr_h), h->truncated_host, 0) == cudaSuccess &&
                 cudaHostGetDevicePointer(reinterpret_cast<void**>(&dn_h), h->done_host, 0) == cudaSuccess) {

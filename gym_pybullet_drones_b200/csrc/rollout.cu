@@ -16,109 +16,99 @@ struct RolloutArgs {
     QsState st;
     QsRolloutIO io;
     QsPolicy pol;        // copy of *io.policy (device pointers inside) when POLICY
+    const float* aw[6];  // actor: {w1 hi, w1 lo, w2 hi, w2 lo, w3 hi, w3 lo}
+    const float* cw[6];  // critic
     int act_type, task, n_envs, D, substeps, N, A, obs_dim, tpb;
     unsigned effects, flags;
     int stage_mode, cap;
 };
 
-// ---- on-device policy: SB3-MlpPolicy-shaped MLP evaluated by ONE WARP per network (warp 0 actor, warp 1 critic) ---------------
-constexpr int kHid = 64, kHidStride = 68;      // hidden rows padded to 68 floats: conflict-free 128-bit reads across 8 rows
+// ---- on-device policy: SB3-MlpPolicy-shaped MLP on the tensor cores, fp32-accurate ------------------------------------------------
+// Y[32 aviaries][64 units] = X[32][K] W[K][64] per layer and warp, as mma.sync.m16n8k8 TF32 tiles with the 3xTF32 split:
+// x = x_hi + x_lo, w = w_hi + w_lo (each part exactly representable in TF32), x w ~ x_hi w_hi + x_hi w_lo + x_lo w_hi with fp32
+// accumulation -- relative error ~2^-21 per product, i.e. fp32-level (a plain TF32/BF16 mma has 2^-11 / 2^-8 and fails the 1e-5
+// parity with the fp32 torch network).  The weights are split once on the host (MlpPolicy); the activations are split per
+// fragment load.  K = 144 / 64 and M = 32 rows per warp are far below a tcgen05 tile (M = 128, operands through shared-memory
+// descriptors and TMEM): at 1.8 GFLOP per tick the legacy mma.sync path is already not the bottleneck.
+constexpr int kHid = 64, kHidStride = 68;      // hidden rows padded to 68 floats: conflict-free fragment loads (4 g + t distinct banks)
 
-__device__ __forceinline__ float4 ld4_any(const float* p, bool vec) {
-    if (vec) return *reinterpret_cast<const float4*>(p);
-    return make_float4(p[0], p[1], p[2], p[3]);
+__device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float c[4], const unsigned a[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// y[av][0..63] = act(b + W^T x[av]) for av < n_av (n_av <= 32).  x rows: K floats at stride x_stride in shared memory; W [K][64]
-// row-major in global memory (read through L1: every lane group of a warp and every CTA of the SM reads the same 8 KB..37 KB).
-// Lane = (aviary group ag = lane / 8, unit group ug = lane % 8): 8 aviaries (ag + 4 j) x 8 units (8 ug + u) = 64 accumulators;
-// per 4 k: 8 x-loads + 8 weight loads for 256 FFMA.  May run in place (y_s == x_s, same stride): all reads precede all writes.
-template <bool TANH>
-__device__ __forceinline__ void mlp_layer64(const float* x_s, int x_stride, int K, bool x_vec, const float* __restrict__ W,
-                                            const float* __restrict__ b, float* y_s, int n_av, int lane) {
-    const int ag = lane >> 3, ug = lane & 7;
-    float acc[8][8];
-    {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + 8 * ug)), b1 = __ldg(reinterpret_cast<const float4*>(b + 8 * ug + 4));
+// One layer for MT m-tiles of 16 aviaries (rows row0 .. row0 + 16 MT) and NT n-tiles of 8 units.  x rows: K floats at stride
+// x_stride in shared memory; Whi / Wlo: [Kpad][8 NT] row-major TF32 halves in global memory (through L1), Kpad = K rounded up to 8
+// with zero rows; bias [8 NT].  Result (tanh or identity) to y_s[row][y_stride] (may alias x_s: all reads precede the writes).
+template <int MT, int NT, bool TANH>
+__device__ __forceinline__ void mma_layer(const float* x_s, int x_stride, int K, const float* __restrict__ Whi, const float* __restrict__ Wlo,
+                                          const float* __restrict__ bias, float* y_s, int y_stride, int row0, int n_rows, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    float c[MT][NT][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            acc[j][0] = b0.x; acc[j][1] = b0.y; acc[j][2] = b0.z; acc[j][3] = b0.w;
-            acc[j][4] = b1.x; acc[j][5] = b1.y; acc[j][6] = b1.z; acc[j][7] = b1.w;
-        }
+    for (int n = 0; n < NT; ++n) {
+        const float b0 = __ldg(bias + 8 * n + 2 * t), b1 = __ldg(bias + 8 * n + 2 * t + 1);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { c[m][n][0] = b0; c[m][n][1] = b1; c[m][n][2] = b0; c[m][n][3] = b1; }
     }
-    const int K4 = K & ~3;
-    for (int k = 0; k < K4; k += 4) {
-        float4 xv[8];
+    const int ldw = 8 * NT;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        unsigned ahi[MT][4], alo[MT][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int av = ag + 4 * j;
-            xv[j] = av < n_av ? ld4_any(x_s + (size_t)av * x_stride + k, x_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int m = 0; m < MT; ++m) {
+            const int r0 = row0 + 16 * m + g, r1 = r0 + 8;
+            const bool k_lo = k0 + t < K, k_hi = k0 + t + 4 < K;
+            const float a0 = (r0 < n_rows && k_lo) ? x_s[(size_t)r0 * x_stride + k0 + t] : 0.f;
+            const float a1 = (r1 < n_rows && k_lo) ? x_s[(size_t)r1 * x_stride + k0 + t] : 0.f;
+            const float a2 = (r0 < n_rows && k_hi) ? x_s[(size_t)r0 * x_stride + k0 + t + 4] : 0.f;
+            const float a3 = (r1 < n_rows && k_hi) ? x_s[(size_t)r1 * x_stride + k0 + t + 4] : 0.f;
+            tf32_split(a0, ahi[m][0], alo[m][0]); tf32_split(a1, ahi[m][1], alo[m][1]);
+            tf32_split(a2, ahi[m][2], alo[m][2]); tf32_split(a3, ahi[m][3], alo[m][3]);
         }
+        const float* wh = Whi + (size_t)(k0 + t) * ldw + g;
+        const float* wl = Wlo + (size_t)(k0 + t) * ldw + g;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(k + kk) * kHid + 8 * ug));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(k + kk) * kHid + 8 * ug + 4));
+        for (int n = 0; n < NT; ++n) {
+            const unsigned bh0 = __float_as_uint(__ldg(wh + 8 * n)), bh1 = __float_as_uint(__ldg(wh + 4 * ldw + 8 * n));
+            const unsigned bl0 = __float_as_uint(__ldg(wl + 8 * n)), bl1 = __float_as_uint(__ldg(wl + 4 * ldw + 8 * n));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float x = kk == 0 ? xv[j].x : (kk == 1 ? xv[j].y : (kk == 2 ? xv[j].z : xv[j].w));
-                acc[j][0] = fmaf(x, w0.x, acc[j][0]); acc[j][1] = fmaf(x, w0.y, acc[j][1]);
-                acc[j][2] = fmaf(x, w0.z, acc[j][2]); acc[j][3] = fmaf(x, w0.w, acc[j][3]);
-                acc[j][4] = fmaf(x, w1.x, acc[j][4]); acc[j][5] = fmaf(x, w1.y, acc[j][5]);
-                acc[j][6] = fmaf(x, w1.z, acc[j][6]); acc[j][7] = fmaf(x, w1.w, acc[j][7]);
+            for (int m = 0; m < MT; ++m) {
+                mma_tf32(c[m][n], alo[m], bh0, bh1);          // small terms first
+                mma_tf32(c[m][n], ahi[m], bl0, bl1);
+                mma_tf32(c[m][n], ahi[m], bh0, bh1);
             }
         }
     }
-    for (int k = K4; k < K; ++k) {                        // K not a multiple of 4 (A = 1 observations)
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)k * kHid + 8 * ug));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)k * kHid + 8 * ug + 4));
+    __syncwarp();                                            // in-place layers: every read of x precedes the first write of y
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int av = ag + 4 * j;
-            const float x = av < n_av ? x_s[(size_t)av * x_stride + k] : 0.f;
-            acc[j][0] = fmaf(x, w0.x, acc[j][0]); acc[j][1] = fmaf(x, w0.y, acc[j][1]);
-            acc[j][2] = fmaf(x, w0.z, acc[j][2]); acc[j][3] = fmaf(x, w0.w, acc[j][3]);
-            acc[j][4] = fmaf(x, w1.x, acc[j][4]); acc[j][5] = fmaf(x, w1.y, acc[j][5]);
-            acc[j][6] = fmaf(x, w1.z, acc[j][6]); acc[j][7] = fmaf(x, w1.w, acc[j][7]);
-        }
-    }
-    __syncwarp();                                         // in-place layers: every read of x precedes the first write of y
+    for (int m = 0; m < MT; ++m) {
+        const int r0 = row0 + 16 * m + g, r1 = r0 + 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int av = ag + 4 * j;
-        if (av < n_av) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = TANH ? tanhf(acc[j][u]) : acc[j][u];
-            float4* y = reinterpret_cast<float4*>(y_s + (size_t)av * kHidStride + 8 * ug);
-            y[0] = make_float4(v[0], v[1], v[2], v[3]); y[1] = make_float4(v[4], v[5], v[6], v[7]);
+        for (int n = 0; n < NT; ++n) {
+            float v0 = c[m][n][0], v1 = c[m][n][1], v2 = c[m][n][2], v3 = c[m][n][3];
+            if (TANH) { v0 = tanhf(v0); v1 = tanhf(v1); v2 = tanhf(v2); v3 = tanhf(v3); }
+            if (r0 < n_rows) *reinterpret_cast<float2*>(y_s + (size_t)r0 * y_stride + 8 * n + 2 * t) = make_float2(v0, v1);
+            if (r1 < n_rows) *reinterpret_cast<float2*>(y_s + (size_t)r1 * y_stride + 8 * n + 2 * t) = make_float2(v2, v3);
         }
     }
     __syncwarp();
 }
 
-// out[av][j] = b[j] + sum_k h[av][k] W[k][j], j < n_out: lane = aviary, the weights are warp-uniform loads
-__device__ __forceinline__ void mlp_head(const float* h_s, const float* __restrict__ W, const float* __restrict__ b, int n_out,
-                                         float* out_s, int n_av, int lane) {
-    if (lane >= n_av) return;
-    const float* h = h_s + (size_t)lane * kHidStride;
-    for (int j0 = 0; j0 < n_out; j0 += 4) {
-        const int nj = n_out - j0 < 4 ? n_out - j0 : 4;
-        float a0 = __ldg(b + j0), a1 = nj > 1 ? __ldg(b + j0 + 1) : 0.f, a2 = nj > 2 ? __ldg(b + j0 + 2) : 0.f, a3 = nj > 3 ? __ldg(b + j0 + 3) : 0.f;
-        for (int k = 0; k < kHid; k += 4) {
-            const float4 hv = *reinterpret_cast<const float4*>(h + k);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const float x = kk == 0 ? hv.x : (kk == 1 ? hv.y : (kk == 2 ? hv.z : hv.w));
-                const float* w = W + (size_t)(k + kk) * n_out + j0;
-                a0 = fmaf(x, __ldg(w), a0);
-                if (nj > 1) a1 = fmaf(x, __ldg(w + 1), a1);
-                if (nj > 2) a2 = fmaf(x, __ldg(w + 2), a2);
-                if (nj > 3) a3 = fmaf(x, __ldg(w + 3), a3);
-            }
-        }
-        float* o = out_s + (size_t)lane * n_out + j0;
-        o[0] = a0; if (nj > 1) o[1] = a1; if (nj > 2) o[2] = a2; if (nj > 3) o[3] = a3;
-    }
+// One network (in -> 64 tanh -> 64 tanh -> 8 NT3 outputs, of which n_out are real) for MT m-tiles of aviaries starting at row0.
+// out_s rows have stride 8 NT3 floats (padded outputs).
+template <int MT>
+__device__ __forceinline__ void mma_net(const float* x_s, int in_dim, const float* const* W /* hi/lo of the three layers */, const float* b1,
+                                        const float* b2, const float* b3, int nt3, float* h_s, float* out_s, int row0, int n_rows, int lane) {
+    mma_layer<MT, 8, true>(x_s, in_dim, in_dim, W[0], W[1], b1, h_s, kHidStride, row0, n_rows, lane);
+    mma_layer<MT, 8, true>(h_s, kHidStride, kHid, W[2], W[3], b2, h_s, kHidStride, row0, n_rows, lane);
+    if (nt3 == 1) mma_layer<MT, 1, false>(h_s, kHidStride, kHid, W[4], W[5], b3, out_s, 8, row0, n_rows, lane);
+    else if (nt3 == 2) mma_layer<MT, 2, false>(h_s, kHidStride, kHid, W[4], W[5], b3, out_s, 16, row0, n_rows, lane);
+    else mma_layer<MT, 4, false>(h_s, kHidStride, kHid, W[4], W[5], b3, out_s, 32, row0, n_rows, lane);
 }
 
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
@@ -138,7 +128,7 @@ __device__ __forceinline__ void round_to_planes(qs::Drone& d) {
 }
 
 template <int EFF, bool PIDACT, bool POLICY>
-__global__ void __launch_bounds__(POLICY ? 64 : kMaxTPB, POLICY ? 3 : 4) rollout_kernel(const __grid_constant__ RolloutArgs a) {
+__global__ void __launch_bounds__(POLICY ? 64 : kMaxTPB, POLICY ? 7 : 4) rollout_kernel(const __grid_constant__ RolloutArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QsParams& P = a.P;
     const int tpb = a.tpb, D = a.D, A = a.A, od = a.obs_dim, T = a.io.T;
@@ -150,17 +140,21 @@ __global__ void __launch_bounds__(POLICY ? 64 : kMaxTPB, POLICY ? 3 : 4) rollout
     const int rows = (int)((N - c0) < tpb ? (N - c0) : tpb);
     double* red_s = reinterpret_cast<double*>(smem_raw);                               // [tpb][2]
     const int cap = a.cap;
-    const size_t fixed = smem_fixed(cap);
-    double* pos_s = red_s + (size_t)cap * 2;                                           // [tpb][3]
-    unsigned char* oob_s = reinterpret_cast<unsigned char*>(pos_s + (size_t)cap * 3);
-    unsigned char* done_s = oob_s + cap;
+    // POLICY (no DYN+ effects, CTA of 64 drones): a compact fixed part -- red_s [64][2] doubles, oob [64], done [64], mbarrier --
+    // so that 7 CTAs (one wave of 1024 CTAs on 148 SMs) fit into shared memory next to the window and the MLP scratch
+    const size_t fixed = POLICY ? (size_t)(64 * 2 * 8 + 64 + 64 + 16 + 112) : smem_fixed(cap);       // 1280 for POLICY
+    double* pos_s = red_s + (size_t)cap * 2;                                           // [tpb][3] (in-CTA downwash only)
+    unsigned char* oob_s = POLICY ? reinterpret_cast<unsigned char*>(red_s + 128) : reinterpret_cast<unsigned char*>(pos_s + (size_t)cap * 3);
+    unsigned char* done_s = oob_s + (POLICY ? 64 : cap);
     unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(smem_raw + fixed - 16);
     float* stage_s = reinterpret_cast<float*>(smem_raw + fixed);                       // [tpb*od + (T+1)*A] sliding window
     // POLICY: [2 nets][32 aviaries][68] hidden activations, [32][out_dim] means, [32] values, [tpb] log-prob terms, after the window
+    // POLICY scratch after the window: per warp one tile of 16 hidden rows [16][68]; padded action means [n_av][8 nt3]; padded
+    // values [n_av][8]; log-prob terms [64]
     float* pol_s = stage_s + ((((size_t)tpb * od + (size_t)(T + 1) * A) + 3) & ~(size_t)3);
-    float* mean_s = pol_s + 2 * 32 * kHidStride;                                        // [<= 128 aviaries][out_dim]
-    float* val_s = mean_s + (size_t)kMaxTPB * a.pol.out_dim;
-    float* lp_s = val_s + kMaxTPB;
+    float* mean_s = pol_s + 2 * 16 * kHidStride;
+    float* val_s = mean_s + (size_t)(64 / (D < 1 ? 1 : D)) * 8 * a.pol.nt3;
+    float* lp_s = val_s + (size_t)(64 / (D < 1 ? 1 : D)) * 8;
 
     const long long e = live ? i / D : 0;
     const int le = t / D;
@@ -200,20 +194,18 @@ __global__ void __launch_bounds__(POLICY ? 64 : kMaxTPB, POLICY ? 3 : 4) rollout
         if (POLICY) {
             // the aviaries of this CTA: rows [le D, le D + D) of the window = one flattened observation of in_dim floats each
             const int n_av = rows / D, warp = t >> 5, lane = t & 31;
-            const bool x_vec = (A == 4) && ((a.pol.in_dim & 3) == 0);
-            for (int a0 = 0; a0 < n_av; a0 += 32) {           // 32 aviaries per pass (one pass for D >= 2)
-                const int na = n_av - a0 < 32 ? n_av - a0 : 32;
-                const float* x0 = base + (size_t)a0 * a.pol.in_dim;
-                if (warp == 0) {
-                    float* h = pol_s;
-                    mlp_layer64<true>(x0, a.pol.in_dim, a.pol.in_dim, x_vec, a.pol.w1, a.pol.b1, h, na, lane);
-                    mlp_layer64<true>(h, kHidStride, kHid, true, a.pol.w2, a.pol.b2, h, na, lane);
-                    mlp_head(h, a.pol.w3, a.pol.b3, a.pol.out_dim, mean_s + (size_t)a0 * a.pol.out_dim, na, lane);
-                } else if (warp == 1 && a.pol.vw1) {
-                    float* h = pol_s + 32 * kHidStride;
-                    mlp_layer64<true>(x0, a.pol.in_dim, a.pol.in_dim, x_vec, a.pol.vw1, a.pol.vb1, h, na, lane);
-                    mlp_layer64<true>(h, kHidStride, kHid, true, a.pol.vw2, a.pol.vb2, h, na, lane);
-                    mlp_head(h, a.pol.vw3, a.pol.vb3, 1, val_s + a0, na, lane);
+            const int ost = 8 * a.pol.nt3;                        // padded width of the output rows in mean_s
+            // 16 aviaries (one m-tile) per warp and call: warp 0 runs the actor, warp 1 the critic, over the same tiles; without a
+            // critic the two warps alternate tiles of the actor.  Hidden rows: one [16][68] tile per warp, overwritten in place.
+            float* hid = pol_s + (size_t)warp * 16 * kHidStride;
+            for (int r0 = 0; r0 < n_av; r0 += 16) {
+                const float* x0 = base + (size_t)r0 * a.pol.in_dim;
+                const int na = n_av - r0;                         // rows of this tile that exist (mma_layer clips at 16)
+                if (a.pol.vw1) {
+                    if (warp == 0) mma_net<1>(x0, a.pol.in_dim, a.aw, a.pol.b1, a.pol.b2, a.pol.b3, a.pol.nt3, hid, mean_s + (size_t)r0 * ost, 0, na, lane);
+                    else if (warp == 1) mma_net<1>(x0, a.pol.in_dim, a.cw, a.pol.vb1, a.pol.vb2, a.pol.vb3, 1, hid, val_s + (size_t)r0 * 8, 0, na, lane);
+                } else if (warp == ((r0 >> 4) & 1)) {
+                    mma_net<1>(x0, a.pol.in_dim, a.aw, a.pol.b1, a.pol.b2, a.pol.b3, a.pol.nt3, hid, mean_s + (size_t)r0 * ost, 0, na, lane);
                 }
             }
             __syncthreads();
@@ -224,7 +216,7 @@ __global__ void __launch_bounds__(POLICY ? 64 : kMaxTPB, POLICY ? 3 : 4) rollout
                     const int idx = dslot * A + j;
                     const float ls = __ldg(a.pol.log_std + idx);
                     const float eps = a.pol.noise ? __ldg(a.pol.noise + ((long long)k * E + e) * od_out + idx) : 0.f;
-                    const float r = fmaf(expf(ls), eps, mean_s[le * od_out + idx]);
+                    const float r = fmaf(expf(ls), eps, mean_s[le * ost + idx]);
                     raw_act[j] = r;
                     act[j] = fminf(fmaxf(r, -1.f), 1.f);                             // the env clips to its action space
                     lp += -0.5f * eps * eps - ls - 0.91893853320467274f;            // log N(r; mean, std)
@@ -237,7 +229,7 @@ __global__ void __launch_bounds__(POLICY ? 64 : kMaxTPB, POLICY ? 3 : 4) rollout
                 for (int q = 0; q < D; ++q) s_lp += lp_s[t + q];
                 const long long oe = (long long)k * E + e;
                 if (a.pol.logprob) a.pol.logprob[oe] = s_lp;
-                if (a.pol.values && a.pol.vw1) a.pol.values[oe] = val_s[le];
+                if (a.pol.values && a.pol.vw1) a.pol.values[oe] = val_s[le * 8];
             }
         }
         if (live) {
@@ -443,15 +435,19 @@ int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int 
         const QsPolicy& q = *io->policy;
         if (pid_act || (effects & 7u) || a.cap > 64) return fail(QS_ERR_UNSUPPORTED, "qs_rollout: the on-device policy supports RPM / ONE_D_RPM actions, no DYN+ effects, drones_per_env <= 64");
         if (io->actions) return fail(QS_ERR_UNSUPPORTED, "qs_rollout: pass either actions or a policy");
-        if (!q.w1 || !q.b1 || !q.w2 || !q.b2 || !q.w3 || !q.b3 || !q.log_std) return fail(QS_ERR_NULL, "qs_rollout: policy weights are NULL");
+        if (!q.w1 || !q.w1_lo || !q.b1 || !q.w2 || !q.w2_lo || !q.b2 || !q.w3 || !q.w3_lo || !q.b3 || !q.log_std) return fail(QS_ERR_NULL, "qs_rollout: policy weights are NULL");
+        if (q.nt3 != 1 && q.nt3 != 2 && q.nt3 != 4) return fail(QS_ERR_SIZE, "qs_rollout: policy nt3 (padded output tiles of 8) must be 1, 2 or 4");
+        if (q.out_dim > 8 * q.nt3) return fail(QS_ERR_SIZE, "qs_rollout: policy out_dim exceeds the padded output width");
         if (q.in_dim != drones_per_env * a.obs_dim || q.out_dim != drones_per_env * A) return fail(QS_ERR_SIZE, "qs_rollout: policy in_dim/out_dim must be D*obs_dim / D*A");
-        if (q.vw1 && (!q.vb1 || !q.vw2 || !q.vb2 || !q.vw3 || !q.vb3)) return fail(QS_ERR_NULL, "qs_rollout: incomplete critic");
+        if (q.vw1 && (!q.vw1_lo || !q.vb1 || !q.vw2 || !q.vw2_lo || !q.vb2 || !q.vw3 || !q.vw3_lo || !q.vb3)) return fail(QS_ERR_NULL, "qs_rollout: incomplete critic");
         if (q.values && !q.vw1) return fail(QS_ERR_NULL, "qs_rollout: values requested without a critic");
-        for (const float* w : {q.w1, q.b1, q.w2, q.b2, q.vw1, q.vb1, q.vw2, q.vb2})
-            if (w && !aligned16(w)) return fail(QS_ERR_ALIGN, "qs_rollout: policy matrices must be 16-byte aligned");
         a.pol = q;
+        a.aw[0] = q.w1; a.aw[1] = q.w1_lo; a.aw[2] = q.w2; a.aw[3] = q.w2_lo; a.aw[4] = q.w3; a.aw[5] = q.w3_lo;
+        a.cw[0] = q.vw1; a.cw[1] = q.vw1_lo; a.cw[2] = q.vw2; a.cw[3] = q.vw2_lo; a.cw[4] = q.vw3; a.cw[5] = q.vw3_lo;
         threads = 64;                                            // warp 0: actor, warp 1: critic
-        sm += 16 + (size_t)(2 * 32 * kHidStride + kMaxTPB * q.out_dim + 2 * kMaxTPB) * 4;
+        const int n_av_max = 64 / drones_per_env;
+        sm = 1280 + (size_t)a.tpb * a.obs_dim * 4 + (size_t)(io->T + 1) * A * 4 + 32
+           + (size_t)(2 * 16 * kHidStride + n_av_max * 8 * q.nt3 + n_av_max * 8 + 64) * 4 + 16;      // compact fixed part, window, hidden tiles, means, values, log-prob terms
         if (sm > 200 * 1024) return fail(QS_ERR_UNSUPPORTED, "qs_rollout: policy + window exceed shared memory");
         if (sm > 48 * 1024) cudaFuncSetAttribute(rollout_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         rollout_kernel<0, false, true><<<blocks, threads, sm, s>>>(a);

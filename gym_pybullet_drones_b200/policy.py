@@ -2,8 +2,9 @@
 `PPO('MlpPolicy', env)` whose `collect_rollouts` alternates policy.forward and env.step).
 
 `MlpPolicy` holds the weights of an SB3-MlpPolicy-shaped actor (flatten -> 64 tanh -> 64 tanh -> linear mean, state-independent
-`log_std`) and optionally the critic (same trunk shape, one output) in the layout the rollout kernel reads: row-major
-`[in][out]` float32 CUDA tensors.  `rollout(policy=...)` then evaluates it inside the kernel every tick, from the observation
+`log_std`) and optionally the critic (same trunk shape, one output) as row-major `[in][out]` float32 CUDA tensors, plus
+the layout the rollout kernel reads: every matrix split once into its TF32 halves (`hi` = weights rounded to TF32, `lo` =
+the rounded remainder; 3xTF32 tensor-core products then reproduce fp32), rows / last-layer columns zero-padded to 8.  `rollout(policy=...)` then evaluates it inside the kernel every tick, from the observation
 window in shared memory: no policy launch, no action tensor round trip.  `forward_torch` is the same network in plain PyTorch
 fp32 (what a learner would run for the gradient step, and what the tests compare the kernel with)."""
 import ctypes as C
@@ -45,6 +46,31 @@ class MlpPolicy:
             raise ValueError("critic input width differs from the actor's")
         self.log_std = torch.as_tensor(log_std, dtype=torch.float32).to(dev).contiguous().reshape(self.out_dim)
         self.device = dev
+        if self.out_dim > 32:
+            raise ValueError("the on-device policy supports up to 32 action outputs per aviary (D * A)")
+        self.nt3 = 1 if self.out_dim <= 8 else (2 if self.out_dim <= 16 else 4)
+        self._split = {"actor": self._prepare(self.actor, 8 * self.nt3), "critic": None if self.critic is None else self._prepare(self.critic, 8)}
+
+    @staticmethod
+    def _tf32(x):
+        """cvt.rna.tf32.f32: round to nearest (ties away) onto the 10-bit TF32 mantissa; the result is an fp32 with 13 zero bits."""
+        i = x.contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    def _prepare(self, net, last_cols):
+        """[(hi, lo, bias)] x 3 with zero-padded rows (multiple of 8) and last-layer columns."""
+        out = []
+        for k, (w, b) in enumerate(net):
+            rows = (w.shape[0] + 7) // 8 * 8
+            cols = last_cols if k == 2 else w.shape[1]
+            wp = torch.zeros((rows, cols), dtype=torch.float32, device=w.device)
+            wp[:w.shape[0], :w.shape[1]] = w
+            bp = torch.zeros((cols,), dtype=torch.float32, device=w.device)
+            bp[:b.shape[0]] = b
+            hi = self._tf32(wp)
+            lo = self._tf32(wp - hi)
+            out.append((hi.contiguous(), lo.contiguous(), bp.contiguous()))
+        return out
 
     @classmethod
     def from_linear(cls, actor_layers, log_std, critic_layers=None, device=None):
@@ -81,10 +107,13 @@ class MlpPolicy:
     # ---- C struct -------------------------------------------------------------------------------------------------------
     def c_struct(self, noise=None, logprob=None, values=None):
         q = N.QsPolicy()
-        (q.w1, q.b1), (q.w2, q.b2), (q.w3, q.b3) = [(w.data_ptr(), b.data_ptr()) for w, b in self.actor]
+        a = self._split["actor"]
+        (q.w1, q.w1_lo, q.b1), (q.w2, q.w2_lo, q.b2), (q.w3, q.w3_lo, q.b3) = [(h.data_ptr(), l.data_ptr(), b.data_ptr()) for h, l, b in a]
         q.log_std = self.log_std.data_ptr()
         if self.critic is not None:
-            (q.vw1, q.vb1), (q.vw2, q.vb2), (q.vw3, q.vb3) = [(w.data_ptr(), b.data_ptr()) for w, b in self.critic]
+            c = self._split["critic"]
+            (q.vw1, q.vw1_lo, q.vb1), (q.vw2, q.vw2_lo, q.vb2), (q.vw3, q.vw3_lo, q.vb3) = [(h.data_ptr(), l.data_ptr(), b.data_ptr()) for h, l, b in c]
+        q.nt3 = self.nt3
         q.noise = None if noise is None else noise.data_ptr()
         q.logprob = None if logprob is None else logprob.data_ptr()
         q.values = None if values is None else values.data_ptr()

@@ -184,18 +184,21 @@ int qs_wait_flags(const unsigned* flags, unsigned seq, int world, unsigned* err_
 /* On-device policy for qs_rollout (the caller is SB3's collect_rollouts, examples/learn.py:67-95): an
  * SB3-MlpPolicy-shaped actor -- flatten(the aviary's [D][obs_dim] observation) -> 64 tanh -> 64 tanh -> linear mean, state
  * independent log_std, Gaussian sample, clip to [-1, 1] for the env -- and optionally the critic (same shape, 1 output),
- * evaluated inside the rollout kernel from the observation window in shared memory (FP32 FFMA, weights through L1).
- * Weight matrices are row-major [in][out] float32 (torch.nn.Linear.weight transposed), device pointers. */
+ * evaluated inside the rollout kernel from the observation window in shared memory on the tensor cores with the 3xTF32
+ * split (fp32-level accuracy).  Every weight matrix is given as TWO row-major [rows_padded][cols_padded] float32 arrays:
+ * `w` = the weights rounded to TF32 (cvt.rna), `w_lo` = (weights - w) rounded to TF32; rows padded with zeros to a multiple
+ * of 8, the last layer's columns to 8 * nt3 (8 for the critic).  gym_pybullet_drones_b200/policy.py prepares them. */
 typedef struct QsPolicy {
-    const float *w1, *b1;      /* [in_dim][64], [64]   in_dim = D * obs_dim */
-    const float *w2, *b2;      /* [64][64], [64] */
-    const float *w3, *b3;      /* [64][out_dim], [out_dim]   out_dim = D * A */
-    const float* log_std;      /* [out_dim] */
-    const float *vw1, *vb1, *vw2, *vb2, *vw3, *vb3;   /* critic [in_dim][64], [64][64], [64][1]; all NULL = no critic */
+    const float *w1, *w1_lo, *b1;      /* [in_dim -> mult. of 8][64], [64]   in_dim = D * obs_dim */
+    const float *w2, *w2_lo, *b2;      /* [64][64], [64] */
+    const float *w3, *w3_lo, *b3;      /* [64][8 nt3], [8 nt3]   out_dim = D * A real columns */
+    const float* log_std;              /* [out_dim] */
+    const float *vw1, *vw1_lo, *vb1, *vw2, *vw2_lo, *vb2, *vw3, *vw3_lo, *vb3;   /* critic [..][64], [64][64], [64][8]; all NULL = no critic */
     const float* noise;        /* [T][E][out_dim] standard-normal draws (e.g. torch.randn), or NULL: action = mean */
     float* logprob;            /* out [T][E] log-probability of the sampled (unclipped) action; nullable */
     float* values;             /* out [T][E] critic output; nullable (required NULL without a critic) */
     int in_dim, out_dim;
+    int nt3, pad_;             /* padded action outputs = 8 * nt3 (nt3 = 1, 2 or 4) */
 } QsPolicy;
 
 /* Multi-tick rollout: T control ticks in ONE launch (the caller is SB3's collect_rollouts,

@@ -1,0 +1,102 @@
+"""Regenerates the round-2 part of profiles/README.md from the bench / config JSON files under profiles/ (run in the build container).
+    python tools/make_profiles_readme_r02.py gpurun_out/<bench>.json [gpurun_out/configs_r02.json]"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+b = json.load(open(sys.argv[1]))
+json.dump(b, open(os.path.join(P, "r02_bench_n1.json"), "w"), indent=1)
+cfg = {}
+if len(sys.argv) > 2 and os.path.isfile(sys.argv[2]):
+    cfg = json.load(open(sys.argv[2]))
+    json.dump(cfg, open(os.path.join(P, "r02_configs.json"), "w"), indent=1)
+elif os.path.isfile(os.path.join(P, "r02_configs.json")):
+    cfg = json.load(open(os.path.join(P, "r02_configs.json")))
+
+
+def load(name):
+    try:
+        return json.load(open(os.path.join(P, name)))
+    except Exception:
+        return None
+
+
+L = ["# profiles/ — measurements (B200, sm_100a)", "",
+     "Round 2 first; the round-1 tables follow unchanged below.  Files are copied from `gpurun_out/` (scratch) by",
+     "`tools/make_profiles_readme_r02.py` / `tools/summarize_profile.py`.", "",
+     "## Round 2: headline bench line (`python bench.py`, N=1; file `r02_bench_n1.json`)", ""]
+r, e = b["roofline"], b["e2e"]
+L += ["| quantity | value |", "|---|---|",
+      "| workload | %s |" % b["config"]["workload"],
+      "| `value` (device-resident, median of %d windows of %d steps) | **%.3g drone-steps/s** (%.2f us per 65 536-drone step) |" % (b["timed_windows"]["count"], b["steps"], b["value"], b["ms_per_step"] * 1e3),
+      "| `roofline.frac` (launch period of back-to-back launches) | achieved %.0f GB/s of %.0f GB/s measured = **%.3f** (646 B x 65 536 / %.2f us) |" % (r["achieved"], r["peak"], r["frac"], r["kernel_ms"] * 1e3),
+      "| `roofline.frac_isolated` (events around single launches after a sync + L2 scrub) | **%.3f** (%.2f us incl. launch/event gap; under ncu: 14.3 us = 0.45, `r02_a_step_fast_kernel_ncu.md`) |" % (r["frac_isolated"], r["kernel_ms_isolated"] * 1e3),
+      "| `roofline.traffic` (ncu dram bytes per launch) | %s |" % (("%.1f MB (reads 26.9 MB inside the kernel + ~27 MB of stores drained from the write-back L2 later; `r02_step_traffic.json`)" % (r["traffic"] / 1e6)) if r.get("traffic") else "null"),
+      "| `e2e` (NumPy API, H2D %d B + D2H %d B per step) | **%.3g drone-steps/s** (%.3f ms per step, %.1f of %.1f GB/s measured in the same run: `pcie_frac` %.2f) |" % (e["h2d_bytes_per_step"], e["d2h_bytes_per_step"], e["value"], e["ms_per_step"], e["d2h_gbs"], e["pcie_d2h_gbs_measured"], e["pcie_frac"]),
+      "| clocks during the timed region | %s |" % json.dumps(b.get("clocks"))]
+if "head_only_mode" in e and "value" in e["head_only_mode"]:
+    L.append("| extra: `host_obs='head'` (12-float heads only) | %.3g drone-steps/s (%.3f ms per step) |" % (e["head_only_mode"]["value"], e["head_only_mode"]["ms_per_step"]))
+if "cpu_baseline" in b:
+    L.append("| `cpu_baseline` (oracle port, 1 core of the GPU box) | %.3g drone-steps/s — %s |" % (b["cpu_baseline"]["value"], b["cpu_baseline"]["sample"]))
+L += ["", "### extras of the same run", "", "| item | us per step | drone-steps/s | algorithmic-bytes fraction of HBM peak / note |", "|---|---|---|---|"]
+ex = b.get("extras", {})
+for k, v in ex.items():
+    if not isinstance(v, dict):
+        L.append("| %s | %.2f | | host cost of one `env.step(tensor)` call on an idle GPU |" % (k, v))
+        continue
+    if k == "drones_per_launch_sweep":
+        for n, w in v.items():
+            if "ms_per_step" in w:
+                L.append("| step kernel at %s drones per launch | %.2f | %.3g | %.3f |" % (n, w["ms_per_step"] * 1e3, w["value"], w["hbm_frac"]))
+        continue
+    if k == "config2_hover_pid_4096" and "per_launch_ms" in v:
+        L.append("| config 2 (4096 x Hover + embedded PID), per launch | %.2f | %.3g | launch-latency bound |" % (v["per_launch_ms"] * 1e3, v["per_launch_value"]))
+        L.append("| config 2 through `qs_rollout` (32 ticks per launch) | %.2f | %.3g | %.3f |" % (v["rollout_T32_ms_per_tick"] * 1e3, v["rollout_value"], v["rollout_hbm_frac"]))
+        continue
+    ms = v.get("ms_per_step", v.get("ms_per_tick"))
+    if ms is None:
+        L.append("| %s | - | - | %s |" % (k, v.get("error", "")))
+        continue
+    frac = v.get("hbm_frac", v.get("hbm_frac_algorithmic"))
+    note = ("%.3f" % frac) if frac is not None else ""
+    if "mlp_tflops_fp32" in v:
+        note = "%.1f TFLOP/s fp32 in the MLP; %s" % (v["mlp_tflops_fp32"], v.get("note", ""))
+    L.append("| %s | %.2f | %.3g | %s |" % (k, ms * 1e3, v["value"], note))
+for name, n in (("r02_bench_n2_own_run.json", 2), ("r02_bench_n8_own_run.json", 8)):
+    d = load(name)
+    if d:
+        L += ["", "### own %d-GPU run (`%s`)" % (n, name), "",
+              "`value` %.3g drone-steps/s (%.2f us per step per rank; per-rank %s), `e2e` %.3g (%.3f ms per step; pinned D2H alone measured at %.1f GB/s per GPU with all ranks active)." %
+              (d["value"], d["ms_per_step"] * 1e3, ", ".join("%.3g" % x for x in d["per_rank_value"]), d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["pcie_d2h_gbs_measured"])]
+for name in ("r02_fused_gather_2gpu.json", "r02_fused_gather_8gpu.json"):
+    d = load(name)
+    if d:
+        L += ["", "### fused observation gather, %d GPUs (`%s`, `tools/gather_multi_gpu.py`)" % (d["world"], name), "",
+              "bit-identical to NCCL `all_gather_into_tensor`: %s; a tick as the learner sees it: step only %.1f us, **fused gather %.1f us**, step + NCCL all-gather %.1f us; learner inbound %.1f MB per tick = %.0f GB/s fused vs %.0f GB/s NCCL (peer-copy peak measured on this pool: 770 GB/s)." %
+              (d["fused_equals_nccl_all_gather"], d["ms_per_tick_step_only"] * 1e3, d["ms_per_tick_fused_gather"] * 1e3, d["ms_per_tick_step_plus_nccl_all_gather_obs"] * 1e3,
+               d["learner_inbound_bytes_per_tick"] / 1e6, d["fused_inbound_GBps"], d["nccl_inbound_GBps"])]
+if cfg:
+    L += ["", "### other BASELINE.json configs (`tools/bench_configs.py`, file `r02_configs.json`)", "",
+          "| config | ms per step / call | per second | alg. bytes | HBM frac (algorithmic) | note |", "|---|---|---|---|---|---|"]
+    for k, v in cfg.items():
+        ms = v.get("ms_per_step", v.get("ms_per_call"))
+        rate = v.get("drone_steps_per_s", v.get("calls_per_s"))
+        extra = v.get("note", "")
+        if "hbm_frac_actual_bytes" in v:
+            extra = "%.3f of the copy peak on the %d bytes actually moved; FP64-bound" % (v["hbm_frac_actual_bytes"], v["actual_bytes"])
+        if "downwash_ms" in v:
+            extra = "downwash kernel: " + ", ".join("%s %.3f ms" % kv for kv in v["downwash_ms"].items())
+        L.append("| %s | %.4f | %.3g | %s | %s | %s |" % (k, ms, rate, v.get("alg_bytes", "-"), ("%.3f" % v["hbm_frac"]) if "hbm_frac" in v else "-", extra))
+L += ["", "### round-2 profile files", "",
+      "* `r02_a_step_fast_kernel_ncu.md` — ncu `--set full` of `step_fast_kernel<4,1,1,1,1>` at 65 536 drones (14.3 us serialised, 110 registers, FP64 pipe 25 %, issue 36 %, DRAM reads 26.9 MB = exactly state + action + span)",
+      "* `r02_step_traffic.json` — the DRAM traffic figure behind `roofline.traffic`",
+      "* `r02_step_timeline.md` — per-warp `%globaltimer` phase timeline of the fast kernel (pipelined, isolated, inter-grid gaps)",
+      "* `r02_bench_n1.json`, `r02_bench_n2_own_run.json`, `r02_bench_n8_own_run.json`, `r02_configs.json`, `r02_fused_gather_{2,8}gpu.json`", ""]
+old = open(os.path.join(P, "README.md")).read()
+marker = "# profiles/ — round 1 measurements (B200, sm_100a)"
+if marker in old:
+    old = old[old.index(marker):]
+open(os.path.join(P, "README.md"), "w").write("\n".join(L) + "\n---\n\n" + old)
+print("wrote profiles/README.md")
