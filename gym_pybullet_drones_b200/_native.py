@@ -77,8 +77,7 @@ class QsRolloutIO(C.Structure):
 
 
 class QsPolicy(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("w1", "w1_lo", "b1", "w2", "w2_lo", "b2", "w3", "w3_lo", "b3", "log_std",
-                                          "vw1", "vw1_lo", "vb1", "vw2", "vw2_lo", "vb2", "vw3", "vw3_lo", "vb3",
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "w2", "b2", "w3", "b3", "log_std", "vw1", "vb1", "vw2", "vb2", "vw3", "vb3",
                                           "noise", "logprob", "values")] + [("in_dim", C.c_int), ("out_dim", C.c_int), ("nt3", C.c_int), ("pad_", C.c_int)]
 
 

@@ -1,5 +1,6 @@
 // rollout.cu -- qs_rollout: T fused control ticks per launch.
 #include "qs_common.cuh"
+#include <cuda_fp16.h>
 
 using namespace qsi;
 
@@ -16,99 +17,186 @@ struct RolloutArgs {
     QsState st;
     QsRolloutIO io;
     QsPolicy pol;        // copy of *io.policy (device pointers inside) when POLICY
-    const float* aw[6];  // actor: {w1 hi, w1 lo, w2 hi, w2 lo, w3 hi, w3 lo}
-    const float* cw[6];  // critic
     int act_type, task, n_envs, D, substeps, N, A, obs_dim, tpb;
     unsigned effects, flags;
     int stage_mode, cap;
 };
 
 // ---- on-device policy: SB3-MlpPolicy-shaped MLP on the tensor cores, fp32-accurate ------------------------------------------------
-// Y[32 aviaries][64 units] = X[32][K] W[K][64] per layer and warp, as mma.sync.m16n8k8 TF32 tiles with the 3xTF32 split:
-// x = x_hi + x_lo, w = w_hi + w_lo (each part exactly representable in TF32), x w ~ x_hi w_hi + x_hi w_lo + x_lo w_hi with fp32
-// accumulation -- relative error ~2^-21 per product, i.e. fp32-level (a plain TF32/BF16 mma has 2^-11 / 2^-8 and fails the 1e-5
-// parity with the fp32 torch network).  The weights are split once on the host (MlpPolicy); the activations are split per
-// fragment load.  K = 144 / 64 and M = 32 rows per warp are far below a tcgen05 tile (M = 128, operands through shared-memory
-// descriptors and TMEM): at 1.8 GFLOP per tick the legacy mma.sync path is already not the bottleneck.
-constexpr int kHid = 64, kHidStride = 68;      // hidden rows padded to 68 floats: conflict-free fragment loads (4 g + t distinct banks)
+// One warp takes 16 aviaries (one m-tile) through the whole network: Y[16][64] = X[16][K] W[K][64] per layer as mma.sync.m16n8k16
+// F16 tiles with a two-term split of both operands: x = x_hi + x_lo, w = w_hi + w_lo with x_hi = fp16(x) and
+// x_lo' = fp16(2^11 (x - x_hi)) (the scaling keeps the remainder out of the fp16 subnormals), and
+//     x w ~ x_hi w_hi + 2^-11 (x_hi w_lo' + x_lo' w_hi)
+// with fp32 accumulation in two accumulator sets -- relative error ~2^-21 per product, i.e. fp32-level (a plain F16/TF32/BF16 mma has
+// 2^-11 / 2^-8 and fails the 1e-5 parity with the fp32 torch network).  FP16 and TF32 carry the same 11 significant bits, but one
+// m16n8k16 F16 instruction does twice the work of an m16n8k8 TF32 one at the same issue rate (8 cycles per SM sub-partition,
+// tools/mma_rate.cu): 3 instead of 6 mma per 16x8x16 block.
+//  * Weights: split once on the host (MlpPolicy) and stored in FRAGMENT ORDER, [k-step][n-tile][lane] x 16 bytes = the lane's
+//    {b0 hi, b1 hi, b0 lo', b1 lo'} registers, so a B fragment is one fully coalesced 128-bit load (L1-resident: the CTAs use
+//    ~160 KB of the SM's 256 KB as shared memory, the actor's 55 KB of weights stay in the rest).
+//  * First layer: the observation rows are read from the shared-memory window as 128-bit loads -- lane t supplies elements
+//    4t .. 4t+3 of each 16-wide k-step instead of the canonical {2t, 2t+1, 2t+8, 2t+9}; W1 is packed with the same permutation of
+//    k, so the product is unchanged -- and split per fragment (conversions saturate to +-65504: an observation beyond that range
+//    acts like a clipped one).
+//  * Hidden layers never leave the registers: the accumulator fragment of n-tiles (2j, 2j+1) IS the A fragment of k-step j of the
+//    next layer (tanh, split, pack) -- no shared-memory round trip, no barrier between layers.
+// K = 144 / 64 and M = 32 rows per CTA are far below a tcgen05 tile (M = 128 per CTA, operands through shared-memory descriptors,
+// accumulators in TMEM) -- see DESIGN.md 4.1b for the numbers.
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 
-__device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+__device__ __forceinline__ unsigned pack_f16x2_sat(float lo_elem, float hi_elem) {
+    unsigned r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
 }
-__device__ __forceinline__ void mma_tf32(float c[4], const unsigned a[4], unsigned b0, unsigned b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+// (x0, x1) -> packed halves of the leading parts and of the scaled remainders
+__device__ __forceinline__ void f16_split2(float x0, float x1, unsigned& hi, unsigned& lo) {
+    hi = pack_f16x2_sat(x0, x1);
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = pack_f16x2_sat((x0 - f.x) * kLoScale, (x1 - f.y) * kLoScale);
 }
+__device__ __forceinline__ void mma_f16(float c[4], const unsigned a[4], unsigned b0, unsigned b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the special-function unit: absolute error ~2e-7 (the libm tanhf costs ~4x the instructions)
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
-// One layer for MT m-tiles of 16 aviaries (rows row0 .. row0 + 16 MT) and NT n-tiles of 8 units.  x rows: K floats at stride
-// x_stride in shared memory; Whi / Wlo: [Kpad][8 NT] row-major TF32 halves in global memory (through L1), Kpad = K rounded up to 8
-// with zero rows; bias [8 NT].  Result (tanh or identity) to y_s[row][y_stride] (may alias x_s: all reads precede the writes).
-template <int MT, int NT, bool TANH>
-__device__ __forceinline__ void mma_layer(const float* x_s, int x_stride, int K, const float* __restrict__ Whi, const float* __restrict__ Wlo,
-                                          const float* __restrict__ bias, float* y_s, int y_stride, int row0, int n_rows, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    float c[MT][NT][4];
+// G n-tiles from n0 against one A fragment: three sweeps, so that no mma waits for the one issued just before it
+template <int G>
+__device__ __forceinline__ void mma_group(float (*c)[4], float (*cx)[4], const unsigned (&ah)[4], const unsigned (&al)[4], const uint4 (&b)[G]) {
+#pragma unroll
+    for (int n = 0; n < G; ++n) mma_f16(cx[n], al, b[n].x, b[n].y);          // x_lo' w_hi
+#pragma unroll
+    for (int n = 0; n < G; ++n) mma_f16(c[n], ah, b[n].x, b[n].y);           // x_hi  w_hi
+#pragma unroll
+    for (int n = 0; n < G; ++n) mma_f16(cx[n], ah, b[n].z, b[n].w);          // x_hi  w_lo'
+}
+template <int G>
+__device__ __forceinline__ void load_bfrag(uint4 (&b)[G], const uint4* __restrict__ W) {
+#pragma unroll
+    for (int n = 0; n < G; ++n) b[n] = __ldg(W + 32 * n);
+}
+template <int NT>
+__device__ __forceinline__ void init_acc(float (&c)[NT][4], float (&cx)[NT][4], const float* __restrict__ bias, int t) {
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
-        const float b0 = __ldg(bias + 8 * n + 2 * t), b1 = __ldg(bias + 8 * n + 2 * t + 1);
-#pragma unroll
-        for (int m = 0; m < MT; ++m) { c[m][n][0] = b0; c[m][n][1] = b1; c[m][n][2] = b0; c[m][n][3] = b1; }
+        const float2 b = __ldg(reinterpret_cast<const float2*>(bias + 8 * n + 2 * t));
+        c[n][0] = b.x; c[n][1] = b.y; c[n][2] = b.x; c[n][3] = b.y;
+        cx[n][0] = 0.f; cx[n][1] = 0.f; cx[n][2] = 0.f; cx[n][3] = 0.f;
     }
-    const int ldw = 8 * NT;
-    for (int k0 = 0; k0 < K; k0 += 8) {
-        unsigned ahi[MT][4], alo[MT][4];
+}
+// accumulators of a 64-unit hidden layer -> tanh -> the 4 k-steps of A fragments of the next layer
+__device__ __forceinline__ void hidden_to_afrag(const float (&c)[8][4], const float (&cx)[8][4], unsigned (&hh)[4][4], unsigned (&hl)[4][4]) {
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            const int r0 = row0 + 16 * m + g, r1 = r0 + 8;
-            const bool k_lo = k0 + t < K, k_hi = k0 + t + 4 < K;
-            const float a0 = (r0 < n_rows && k_lo) ? x_s[(size_t)r0 * x_stride + k0 + t] : 0.f;
-            const float a1 = (r1 < n_rows && k_lo) ? x_s[(size_t)r1 * x_stride + k0 + t] : 0.f;
-            const float a2 = (r0 < n_rows && k_hi) ? x_s[(size_t)r0 * x_stride + k0 + t + 4] : 0.f;
-            const float a3 = (r1 < n_rows && k_hi) ? x_s[(size_t)r1 * x_stride + k0 + t + 4] : 0.f;
-            tf32_split(a0, ahi[m][0], alo[m][0]); tf32_split(a1, ahi[m][1], alo[m][1]);
-            tf32_split(a2, ahi[m][2], alo[m][2]); tf32_split(a3, ahi[m][3], alo[m][3]);
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int n = 2 * j + h;
+            const float v0 = tanh_fast(fmaf(cx[n][0], kLoInv, c[n][0])), v1 = tanh_fast(fmaf(cx[n][1], kLoInv, c[n][1]));
+            const float v2 = tanh_fast(fmaf(cx[n][2], kLoInv, c[n][2])), v3 = tanh_fast(fmaf(cx[n][3], kLoInv, c[n][3]));
+            f16_split2(v0, v1, hh[j][2 * h], hl[j][2 * h]);                  // row g
+            f16_split2(v2, v3, hh[j][2 * h + 1], hl[j][2 * h + 1]);          // row g + 8
         }
-        const float* wh = Whi + (size_t)(k0 + t) * ldw + g;
-        const float* wl = Wlo + (size_t)(k0 + t) * ldw + g;
-#pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            const unsigned bh0 = __float_as_uint(__ldg(wh + 8 * n)), bh1 = __float_as_uint(__ldg(wh + 4 * ldw + 8 * n));
-            const unsigned bl0 = __float_as_uint(__ldg(wl + 8 * n)), bl1 = __float_as_uint(__ldg(wl + 4 * ldw + 8 * n));
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                mma_tf32(c[m][n], alo[m], bh0, bh1);          // small terms first
-                mma_tf32(c[m][n], ahi[m], bl0, bl1);
-                mma_tf32(c[m][n], ahi[m], bh0, bh1);
-            }
-        }
-    }
-    __syncwarp();                                            // in-place layers: every read of x precedes the first write of y
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-        const int r0 = row0 + 16 * m + g, r1 = r0 + 8;
-#pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            float v0 = c[m][n][0], v1 = c[m][n][1], v2 = c[m][n][2], v3 = c[m][n][3];
-            if (TANH) { v0 = tanhf(v0); v1 = tanhf(v1); v2 = tanhf(v2); v3 = tanhf(v3); }
-            if (r0 < n_rows) *reinterpret_cast<float2*>(y_s + (size_t)r0 * y_stride + 8 * n + 2 * t) = make_float2(v0, v1);
-            if (r1 < n_rows) *reinterpret_cast<float2*>(y_s + (size_t)r1 * y_stride + 8 * n + 2 * t) = make_float2(v2, v3);
-        }
-    }
-    __syncwarp();
 }
 
-// One network (in -> 64 tanh -> 64 tanh -> 8 NT3 outputs, of which n_out are real) for MT m-tiles of aviaries starting at row0.
-// out_s rows have stride 8 NT3 floats (padded outputs).
-template <int MT>
-__device__ __forceinline__ void mma_net(const float* x_s, int in_dim, const float* const* W /* hi/lo of the three layers */, const float* b1,
-                                        const float* b2, const float* b3, int nt3, float* h_s, float* out_s, int row0, int n_rows, int lane) {
-    mma_layer<MT, 8, true>(x_s, in_dim, in_dim, W[0], W[1], b1, h_s, kHidStride, row0, n_rows, lane);
-    mma_layer<MT, 8, true>(h_s, kHidStride, kHid, W[2], W[3], b2, h_s, kHidStride, row0, n_rows, lane);
-    if (nt3 == 1) mma_layer<MT, 1, false>(h_s, kHidStride, kHid, W[4], W[5], b3, out_s, 8, row0, n_rows, lane);
-    else if (nt3 == 2) mma_layer<MT, 2, false>(h_s, kHidStride, kHid, W[4], W[5], b3, out_s, 16, row0, n_rows, lane);
-    else mma_layer<MT, 4, false>(h_s, kHidStride, kHid, W[4], W[5], b3, out_s, 32, row0, n_rows, lane);
+// One network (in -> 64 tanh -> 64 tanh -> 8 nt3 outputs) for 16 aviaries, by one warp.  x_s: rows of in_dim fp32 values in shared
+// memory (rows past n_rows repeat the last row; their outputs are not stored); W1/W2/W3: fragment-ordered weights (see above; W1 with
+// the 4t permutation); out_s rows have stride 8 nt3 floats (padded outputs).
+__device__ __forceinline__ void warp_net(const float* x_s, int in_dim, const uint4* __restrict__ W1, const uint4* __restrict__ W2,
+                                         const uint4* __restrict__ W3, const float* b1, const float* b2, const float* b3, int nt3, float* out_s,
+                                         int n_rows, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    unsigned hh[4][4], hl[4][4];
+    {   // ---- layer 1: K = in_dim from shared memory ----
+        float c[8][4], cx[8][4];
+        init_acc<8>(c, cx, b1, t);
+        const int last = n_rows - 1;
+        const float* p0 = x_s + (size_t)(g < last ? g : last) * in_dim + 4 * t;
+        const float* p1 = x_s + (size_t)(g + 8 < last ? g + 8 : last) * in_dim + 4 * t;
+        const bool vec4 = ((reinterpret_cast<size_t>(x_s) & 15) == 0) && ((in_dim & 3) == 0);
+        const uint4* w = W1 + lane;
+        uint4 ba[4], bb[4];
+        load_bfrag<4>(ba, w);
+#pragma unroll 1
+        for (int k0 = 0; k0 < in_dim; k0 += 16, w += 8 * 32) {
+            load_bfrag<4>(bb, w + 4 * 32);
+            unsigned ah[4], al[4];
+            if (vec4 && k0 + 16 <= in_dim) {
+                const float4 u = *reinterpret_cast<const float4*>(p0 + k0), v = *reinterpret_cast<const float4*>(p1 + k0);
+                f16_split2(u.x, u.y, ah[0], al[0]); f16_split2(v.x, v.y, ah[1], al[1]);
+                f16_split2(u.z, u.w, ah[2], al[2]); f16_split2(v.z, v.w, ah[3], al[3]);
+            } else {                                         // unaligned rows (odd action width) or the ragged last k-step: elements past
+                const int ka = k0 + 4 * t;                   // in_dim are zeros (their weights are zero rows)
+                const float* q0 = p0 + k0; const float* q1 = p1 + k0;
+                f16_split2(ka < in_dim ? q0[0] : 0.f, ka + 1 < in_dim ? q0[1] : 0.f, ah[0], al[0]);
+                f16_split2(ka < in_dim ? q1[0] : 0.f, ka + 1 < in_dim ? q1[1] : 0.f, ah[1], al[1]);
+                f16_split2(ka + 2 < in_dim ? q0[2] : 0.f, ka + 3 < in_dim ? q0[3] : 0.f, ah[2], al[2]);
+                f16_split2(ka + 2 < in_dim ? q1[2] : 0.f, ka + 3 < in_dim ? q1[3] : 0.f, ah[3], al[3]);
+            }
+            mma_group<4>(c, cx, ah, al, ba);
+            if (k0 + 16 < in_dim) load_bfrag<4>(ba, w + 8 * 32);
+            mma_group<4>(c + 4, cx + 4, ah, al, bb);
+        }
+        hidden_to_afrag(c, cx, hh, hl);
+    }
+    {   // ---- layer 2: K = 64 from registers ----
+        float c[8][4], cx[8][4];
+        init_acc<8>(c, cx, b2, t);
+        const uint4* w = W2 + lane;
+        uint4 ba[2], bb[2];
+        load_bfrag<2>(ba, w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int n = 0; n < 8; n += 4) {
+                load_bfrag<2>(bb, w + (8 * j + n + 2) * 32);
+                mma_group<2>(c + n, cx + n, hh[j], hl[j], ba);
+                if (8 * j + n + 4 < 32) load_bfrag<2>(ba, w + (8 * j + n + 4) * 32);
+                mma_group<2>(c + n + 2, cx + n + 2, hh[j], hl[j], bb);
+            }
+        }
+        hidden_to_afrag(c, cx, hh, hl);
+    }
+    // ---- layer 3: K = 64 from registers, one n-tile of 8 outputs at a time ----
+    const int ost = 8 * nt3;
+    for (int n = 0; n < nt3; ++n) {
+        float c[1][4], cx[1][4];
+        init_acc<1>(c, cx, b3 + 8 * n, t);
+        uint4 b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = __ldg(W3 + ((size_t)j * nt3 + n) * 32 + lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            mma_f16(cx[0], hl[j], b[j].x, b[j].y); mma_f16(c[0], hh[j], b[j].x, b[j].y); mma_f16(cx[0], hh[j], b[j].z, b[j].w);
+        }
+        float* o0 = out_s + (size_t)g * ost + 8 * n + 2 * t;
+        if (g < n_rows) *reinterpret_cast<float2*>(o0) = make_float2(fmaf(cx[0][0], kLoInv, c[0][0]), fmaf(cx[0][1], kLoInv, c[0][1]));
+        if (g + 8 < n_rows) *reinterpret_cast<float2*>(o0 + 8 * ost) = make_float2(fmaf(cx[0][2], kLoInv, c[0][2]), fmaf(cx[0][3], kLoInv, c[0][3]));
+    }
+}
+
+// The policy part of one tick for the whole CTA: actor (and critic) over the CTA's aviaries in tiles of 16; work item i = net x tile
+// goes to warp i & 1.  Deliberately NOT inlined: inside the tick loop its ~120 live registers made the compiler spill the drone state
+// in the middle of the physics substeps; as a call, the state is saved once per tick around it.  `parked` is not touched: the caller
+// hands over the address of its drone state so that the state demonstrably lives in local memory across the call (one store + load
+// per tick) instead of being spilled piecemeal inside the substep loop.
+__device__ __noinline__ void policy_forward(const RolloutArgs& a, const float* base, float* mean_s, float* val_s, int n_av, int t, qs::Drone* parked) {
+    if (n_av < 0) parked->px = 0.0;                          // never taken; keeps the hand-over opaque to the optimiser
+    const int warp = t >> 5, lane = t & 31, ost = 8 * a.pol.nt3;
+    const int tiles = (n_av + 15) >> 4, items = a.pol.vw1 ? 2 * tiles : tiles;
+    for (int i = warp; i < items; i += 2) {
+        const bool critic = i >= tiles;
+        const int r0 = 16 * (critic ? i - tiles : i);
+        const float* x0 = base + (size_t)r0 * a.pol.in_dim;
+        if (!critic)
+            warp_net(x0, a.pol.in_dim, reinterpret_cast<const uint4*>(a.pol.w1), reinterpret_cast<const uint4*>(a.pol.w2), reinterpret_cast<const uint4*>(a.pol.w3),
+                     a.pol.b1, a.pol.b2, a.pol.b3, a.pol.nt3, mean_s + (size_t)r0 * ost, n_av - r0, lane);
+        else
+            warp_net(x0, a.pol.in_dim, reinterpret_cast<const uint4*>(a.pol.vw1), reinterpret_cast<const uint4*>(a.pol.vw2), reinterpret_cast<const uint4*>(a.pol.vw3),
+                     a.pol.vb1, a.pol.vb2, a.pol.vb3, 1, val_s + (size_t)r0 * 8, n_av - r0, lane);
+    }
+    __syncthreads();                                         // means / values of every aviary of the CTA are in shared memory
 }
 
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
@@ -148,11 +236,9 @@ __global__ void __launch_bounds__(POLICY ? 64 : kMaxTPB, POLICY ? 7 : 4) rollout
     unsigned char* done_s = oob_s + (POLICY ? 64 : cap);
     unsigned long long* bar_s = reinterpret_cast<unsigned long long*>(smem_raw + fixed - 16);
     float* stage_s = reinterpret_cast<float*>(smem_raw + fixed);                       // [tpb*od + (T+1)*A] sliding window
-    // POLICY: [2 nets][32 aviaries][68] hidden activations, [32][out_dim] means, [32] values, [tpb] log-prob terms, after the window
-    // POLICY scratch after the window: per warp one tile of 16 hidden rows [16][68]; padded action means [n_av][8 nt3]; padded
-    // values [n_av][8]; log-prob terms [64]
+    // POLICY scratch after the window: padded action means [n_av][8 nt3]; padded values [n_av][8]; log-prob terms [64]
     float* pol_s = stage_s + ((((size_t)tpb * od + (size_t)(T + 1) * A) + 3) & ~(size_t)3);
-    float* mean_s = pol_s + 2 * 16 * kHidStride;
+    float* mean_s = pol_s;
     float* val_s = mean_s + (size_t)(64 / (D < 1 ? 1 : D)) * 8 * a.pol.nt3;
     float* lp_s = val_s + (size_t)(64 / (D < 1 ? 1 : D)) * 8;
 
@@ -193,22 +279,13 @@ __global__ void __launch_bounds__(POLICY ? 64 : kMaxTPB, POLICY ? 7 : 4) rollout
         float raw_act[4] = {0.f, 0.f, 0.f, 0.f};
         if (POLICY) {
             // the aviaries of this CTA: rows [le D, le D + D) of the window = one flattened observation of in_dim floats each
-            const int n_av = rows / D, warp = t >> 5, lane = t & 31;
+            const int n_av = rows / D;
             const int ost = 8 * a.pol.nt3;                        // padded width of the output rows in mean_s
-            // 16 aviaries (one m-tile) per warp and call: warp 0 runs the actor, warp 1 the critic, over the same tiles; without a
-            // critic the two warps alternate tiles of the actor.  Hidden rows: one [16][68] tile per warp, overwritten in place.
-            float* hid = pol_s + (size_t)warp * 16 * kHidStride;
-            for (int r0 = 0; r0 < n_av; r0 += 16) {
-                const float* x0 = base + (size_t)r0 * a.pol.in_dim;
-                const int na = n_av - r0;                         // rows of this tile that exist (mma_layer clips at 16)
-                if (a.pol.vw1) {
-                    if (warp == 0) mma_net<1>(x0, a.pol.in_dim, a.aw, a.pol.b1, a.pol.b2, a.pol.b3, a.pol.nt3, hid, mean_s + (size_t)r0 * ost, 0, na, lane);
-                    else if (warp == 1) mma_net<1>(x0, a.pol.in_dim, a.cw, a.pol.vb1, a.pol.vb2, a.pol.vb3, 1, hid, val_s + (size_t)r0 * 8, 0, na, lane);
-                } else if (warp == ((r0 >> 4) & 1)) {
-                    mma_net<1>(x0, a.pol.in_dim, a.aw, a.pol.b1, a.pol.b2, a.pol.b3, a.pol.nt3, hid, mean_s + (size_t)r0 * ost, 0, na, lane);
-                }
+            {
+                qs::Drone parked = d;
+                policy_forward(a, base, mean_s, val_s, n_av, t, &parked);
+                d = parked;
             }
-            __syncthreads();
             float lp = 0.f;
             if (live) {
                 const int od_out = a.pol.out_dim;
@@ -435,19 +512,19 @@ int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int 
         const QsPolicy& q = *io->policy;
         if (pid_act || (effects & 7u) || a.cap > 64) return fail(QS_ERR_UNSUPPORTED, "qs_rollout: the on-device policy supports RPM / ONE_D_RPM actions, no DYN+ effects, drones_per_env <= 64");
         if (io->actions) return fail(QS_ERR_UNSUPPORTED, "qs_rollout: pass either actions or a policy");
-        if (!q.w1 || !q.w1_lo || !q.b1 || !q.w2 || !q.w2_lo || !q.b2 || !q.w3 || !q.w3_lo || !q.b3 || !q.log_std) return fail(QS_ERR_NULL, "qs_rollout: policy weights are NULL");
+        if (!q.w1 || !q.b1 || !q.w2 || !q.b2 || !q.w3 || !q.b3 || !q.log_std) return fail(QS_ERR_NULL, "qs_rollout: policy weights are NULL");
         if (q.nt3 != 1 && q.nt3 != 2 && q.nt3 != 4) return fail(QS_ERR_SIZE, "qs_rollout: policy nt3 (padded output tiles of 8) must be 1, 2 or 4");
         if (q.out_dim > 8 * q.nt3) return fail(QS_ERR_SIZE, "qs_rollout: policy out_dim exceeds the padded output width");
         if (q.in_dim != drones_per_env * a.obs_dim || q.out_dim != drones_per_env * A) return fail(QS_ERR_SIZE, "qs_rollout: policy in_dim/out_dim must be D*obs_dim / D*A");
-        if (q.vw1 && (!q.vw1_lo || !q.vb1 || !q.vw2 || !q.vw2_lo || !q.vb2 || !q.vw3 || !q.vw3_lo || !q.vb3)) return fail(QS_ERR_NULL, "qs_rollout: incomplete critic");
+        if (q.vw1 && (!q.vb1 || !q.vw2 || !q.vb2 || !q.vw3 || !q.vb3)) return fail(QS_ERR_NULL, "qs_rollout: incomplete critic");
         if (q.values && !q.vw1) return fail(QS_ERR_NULL, "qs_rollout: values requested without a critic");
+        if (!aligned16(q.w1) || !aligned16(q.w2) || !aligned16(q.w3) || (q.vw1 && (!aligned16(q.vw1) || !aligned16(q.vw2) || !aligned16(q.vw3))))
+            return fail(QS_ERR_ALIGN, "qs_rollout: policy weight arrays must be 16-byte aligned");
         a.pol = q;
-        a.aw[0] = q.w1; a.aw[1] = q.w1_lo; a.aw[2] = q.w2; a.aw[3] = q.w2_lo; a.aw[4] = q.w3; a.aw[5] = q.w3_lo;
-        a.cw[0] = q.vw1; a.cw[1] = q.vw1_lo; a.cw[2] = q.vw2; a.cw[3] = q.vw2_lo; a.cw[4] = q.vw3; a.cw[5] = q.vw3_lo;
-        threads = 64;                                            // warp 0: actor, warp 1: critic
+        threads = 64;                                            // two warps: 64 drones, 32 hidden units each in the MLP
         const int n_av_max = 64 / drones_per_env;
         sm = 1280 + (size_t)a.tpb * a.obs_dim * 4 + (size_t)(io->T + 1) * A * 4 + 32
-           + (size_t)(2 * 16 * kHidStride + n_av_max * 8 * q.nt3 + n_av_max * 8 + 64) * 4 + 16;      // compact fixed part, window, hidden tiles, means, values, log-prob terms
+           + (size_t)(n_av_max * 8 * q.nt3 + n_av_max * 8 + 64) * 4 + 16;      // compact fixed part, window, means, values, log-prob terms
         if (sm > 200 * 1024) return fail(QS_ERR_UNSUPPORTED, "qs_rollout: policy + window exceed shared memory");
         if (sm > 48 * 1024) cudaFuncSetAttribute(rollout_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         rollout_kernel<0, false, true><<<blocks, threads, sm, s>>>(a);

@@ -3,8 +3,9 @@
 
 `MlpPolicy` holds the weights of an SB3-MlpPolicy-shaped actor (flatten -> 64 tanh -> 64 tanh -> linear mean, state-independent
 `log_std`) and optionally the critic (same trunk shape, one output) as row-major `[in][out]` float32 CUDA tensors, plus
-the layout the rollout kernel reads: every matrix split once into its TF32 halves (`hi` = weights rounded to TF32, `lo` =
-the rounded remainder; 3xTF32 tensor-core products then reproduce fp32), rows / last-layer columns zero-padded to 8.  `rollout(policy=...)` then evaluates it inside the kernel every tick, from the observation
+the layout the rollout kernel reads: every matrix split once into two float16 parts (`hi` = fp16(W), `lo` = fp16(2048 (W - hi));
+the tensor-core products hi*hi + 2^-11 (hi*lo + lo*hi) with fp32 accumulation then reproduce fp32), stored in the order of the
+mma B fragments (one 16-byte load per lane, k-step and 8 outputs), rows zero-padded to a multiple of 16 and last-layer columns to 8.  `rollout(policy=...)` then evaluates it inside the kernel every tick, from the observation
 window in shared memory: no policy launch, no action tensor round trip.  `forward_torch` is the same network in plain PyTorch
 fp32 (what a learner would run for the gradient step, and what the tests compare the kernel with)."""
 import ctypes as C
@@ -52,24 +53,37 @@ class MlpPolicy:
         self._split = {"actor": self._prepare(self.actor, 8 * self.nt3), "critic": None if self.critic is None else self._prepare(self.critic, 8)}
 
     @staticmethod
-    def _tf32(x):
-        """cvt.rna.tf32.f32: round to nearest (ties away) onto the 10-bit TF32 mantissa; the result is an fp32 with 13 zero bits."""
-        i = x.contiguous().view(torch.int32)
-        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    def _fragment_order(hi, lo, first_layer):
+        """[Kpad, Npad] float16 parts -> [Kpad / 16, Npad / 8, 32, 4] int32: per (k-step, n-tile, lane) the lane's B-fragment
+        registers of mma.m16n8k16 {b0 hi, b1 hi, b0 lo', b1 lo'} (include/quadsim.h, QsPolicy).  Lane = 4 g + t holds column 8 n + g
+        and the k pairs (ka, ka + 1), (kb, kb + 1) with (ka, kb) = (2 t, 2 t + 8), or (4 t, 4 t + 2) for the first layer."""
+        K, Nc = hi.shape
+        dev = hi.device
+        lane = torch.arange(32, device=dev)
+        g, t = lane // 4, lane % 4
+        ka, kb = (4 * t, 4 * t + 2) if first_layer else (2 * t, 2 * t + 8)
+        ks = torch.arange(K // 16, device=dev).view(-1, 1, 1) * 16
+        col = (torch.arange(Nc // 8, device=dev).view(1, -1, 1) * 8 + g.view(1, 1, -1)).expand(K // 16, -1, -1)
+
+        def pair(part, k):                                   # {part[k][col], part[k + 1][col]} -> low half, high half
+            u = part.contiguous().view(torch.int16).to(torch.int32) & 0xFFFF
+            rows = (ks + k.view(1, 1, -1)).expand(-1, Nc // 8, -1)
+            return u[rows, col] | (u[rows + 1, col] << 16)
+        return torch.stack([pair(hi, ka), pair(hi, kb), pair(lo, ka), pair(lo, kb)], dim=-1).contiguous()
 
     def _prepare(self, net, last_cols):
-        """[(hi, lo, bias)] x 3 with zero-padded rows (multiple of 8) and last-layer columns."""
+        """[(fragment-ordered weights, bias)] x 3 with zero-padded rows (multiple of 16) and last-layer columns."""
         out = []
         for k, (w, b) in enumerate(net):
-            rows = (w.shape[0] + 7) // 8 * 8
+            rows = (w.shape[0] + 15) // 16 * 16
             cols = last_cols if k == 2 else w.shape[1]
             wp = torch.zeros((rows, cols), dtype=torch.float32, device=w.device)
             wp[:w.shape[0], :w.shape[1]] = w
             bp = torch.zeros((cols,), dtype=torch.float32, device=w.device)
             bp[:b.shape[0]] = b
-            hi = self._tf32(wp)
-            lo = self._tf32(wp - hi)
-            out.append((hi.contiguous(), lo.contiguous(), bp.contiguous()))
+            hi = wp.clamp(-65504.0, 65504.0).to(torch.float16)
+            lo = ((wp - hi.to(torch.float32)) * 2048.0).clamp(-65504.0, 65504.0).to(torch.float16)
+            out.append((self._fragment_order(hi, lo, k == 0), bp.contiguous()))
         return out
 
     @classmethod
@@ -108,11 +122,11 @@ class MlpPolicy:
     def c_struct(self, noise=None, logprob=None, values=None):
         q = N.QsPolicy()
         a = self._split["actor"]
-        (q.w1, q.w1_lo, q.b1), (q.w2, q.w2_lo, q.b2), (q.w3, q.w3_lo, q.b3) = [(h.data_ptr(), l.data_ptr(), b.data_ptr()) for h, l, b in a]
+        (q.w1, q.b1), (q.w2, q.b2), (q.w3, q.b3) = [(w.data_ptr(), b.data_ptr()) for w, b in a]
         q.log_std = self.log_std.data_ptr()
         if self.critic is not None:
             c = self._split["critic"]
-            (q.vw1, q.vw1_lo, q.vb1), (q.vw2, q.vw2_lo, q.vb2), (q.vw3, q.vw3_lo, q.vb3) = [(h.data_ptr(), l.data_ptr(), b.data_ptr()) for h, l, b in c]
+            (q.vw1, q.vb1), (q.vw2, q.vb2), (q.vw3, q.vb3) = [(w.data_ptr(), b.data_ptr()) for w, b in c]
         q.nt3 = self.nt3
         q.noise = None if noise is None else noise.data_ptr()
         q.logprob = None if logprob is None else logprob.data_ptr()

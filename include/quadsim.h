@@ -184,16 +184,25 @@ int qs_wait_flags(const unsigned* flags, unsigned seq, int world, unsigned* err_
 /* On-device policy for qs_rollout (the caller is SB3's collect_rollouts, examples/learn.py:67-95): an
  * SB3-MlpPolicy-shaped actor -- flatten(the aviary's [D][obs_dim] observation) -> 64 tanh -> 64 tanh -> linear mean, state
  * independent log_std, Gaussian sample, clip to [-1, 1] for the env -- and optionally the critic (same shape, 1 output),
- * evaluated inside the rollout kernel from the observation window in shared memory on the tensor cores with the 3xTF32
- * split (fp32-level accuracy).  Every weight matrix is given as TWO row-major [rows_padded][cols_padded] float32 arrays:
- * `w` = the weights rounded to TF32 (cvt.rna), `w_lo` = (weights - w) rounded to TF32; rows padded with zeros to a multiple
- * of 8, the last layer's columns to 8 * nt3 (8 for the critic).  gym_pybullet_drones_b200/policy.py prepares them. */
+ * evaluated inside the rollout kernel from the observation window in shared memory on the tensor cores (mma m16n8k16 F16) with
+ * a two-term split of both operands (fp32-level accuracy: x w ~ x_hi w_hi + 2^-11 (x_hi w_lo' + x_lo' w_hi), fp32 accumulation;
+ * w_hi = fp16(w), w_lo' = fp16(2048 (w - w_hi))).  Observations beyond +-65504 saturate.
+ * Every weight matrix W[in][out] is given in FRAGMENT ORDER: rows padded with zeros to a multiple of 16, columns to a multiple
+ * of 8 (the last layer's to 8 * nt3, the critic's to 8), then [k-step ks][n-tile n][lane l] x 4 words, lane l = 4 g + t:
+ *     word 0 = {w_hi[16 ks + ka][8 n + g], w_hi[16 ks + ka + 1][8 n + g]}   (low half, high half)
+ *     word 1 = {w_hi[16 ks + kb][8 n + g], w_hi[16 ks + kb + 1][8 n + g]}
+ *     word 2, 3 = the same two pairs of w_lo'
+ * with (ka, kb) = (2 t, 2 t + 8) for layers 2 and 3 -- the B fragment of mma.m16n8k16 -- and (ka, kb) = (4 t, 4 t + 2) for
+ * layer 1 (its A operand is read as 4 consecutive observation elements per lane; any permutation of k inside a k-step is
+ * allowed as long as A and B agree).  gym_pybullet_drones_b200/policy.py prepares the arrays (16-byte aligned). */
 typedef struct QsPolicy {
-    const float *w1, *w1_lo, *b1;      /* [in_dim -> mult. of 8][64], [64]   in_dim = D * obs_dim */
-    const float *w2, *w2_lo, *b2;      /* [64][64], [64] */
-    const float *w3, *w3_lo, *b3;      /* [64][8 nt3], [8 nt3]   out_dim = D * A real columns */
-    const float* log_std;              /* [out_dim] */
-    const float *vw1, *vw1_lo, *vb1, *vw2, *vw2_lo, *vb2, *vw3, *vw3_lo, *vb3;   /* critic [..][64], [64][64], [64][8]; all NULL = no critic */
+    const unsigned* w1; const float* b1;      /* [ceil(in_dim / 16)][8][32][4], [64]   in_dim = D * obs_dim */
+    const unsigned* w2; const float* b2;      /* [4][8][32][4], [64] */
+    const unsigned* w3; const float* b3;      /* [4][nt3][32][4], [8 nt3]   out_dim = D * A real columns */
+    const float* log_std;                     /* [out_dim] */
+    const unsigned* vw1; const float* vb1;    /* critic, same arrangement ([..][8], [4][8], [4][1] tiles); all NULL = no critic */
+    const unsigned* vw2; const float* vb2;
+    const unsigned* vw3; const float* vb3;
     const float* noise;        /* [T][E][out_dim] standard-normal draws (e.g. torch.randn), or NULL: action = mean */
     float* logprob;            /* out [T][E] log-probability of the sampled (unclipped) action; nullable */
     float* values;             /* out [T][E] critic output; nullable (required NULL without a critic) */
