@@ -560,8 +560,8 @@ def run_extras(a, envs, acts, gen, dev, world, R, peak_gbs, barrier):
             pms = timed(prol, 10) / T
             macs = (D * OBS_DIM * 64 + 64 * 64 + 64 * D * A) + ((D * OBS_DIM * 64 + 64 * 64 + 64) if critic else 0)
             extras["policy_rollout_" + name] = {"ms_per_tick": pms, "value": DRONES_PER_GPU * world / (pms * 1e-3), "unit": METRIC,
-                                                 "mlp_tflops_fp32": 2 * macs * (DRONES_PER_GPU // D) / (pms * 1e-3) / 1e12,
-                                                 "note": "qs_rollout(policy=MlpPolicy %d-64-64-%d%s): FP32 FFMA inside the rollout kernel, T=%d ticks per launch" % (D * OBS_DIM, D * A, " + critic" if critic else "", T)}
+                                                 "mlp_gflop_per_tick_fp32_equiv": 2e-9 * macs * (DRONES_PER_GPU // D), "mlp_tflops_fp32_equiv": 2 * macs * (DRONES_PER_GPU // D) / (pms * 1e-3) / 1e12,
+                                                 "note": "qs_rollout(policy=MlpPolicy %d-64-64-%d%s): evaluated inside the rollout kernel on the tensor cores (mma.sync m16n8k16 F16, two-term operand split = fp32-level accuracy, 3 mma per fp32-equivalent block), T=%d ticks per launch" % (D * OBS_DIM, D * A, " + critic" if critic else "", T)}
             del hold, noise, pol
     except Exception as ex:  # pragma: no cover
         extras["policy_rollout"] = {"error": repr(ex)}

@@ -115,12 +115,13 @@ __device__ __forceinline__ void warp_net(const float* x_s, int in_dim, const uin
         const float* p0 = x_s + (size_t)(g < last ? g : last) * in_dim + 4 * t;
         const float* p1 = x_s + (size_t)(g + 8 < last ? g + 8 : last) * in_dim + 4 * t;
         const bool vec4 = ((reinterpret_cast<size_t>(x_s) & 15) == 0) && ((in_dim & 3) == 0);
+        // four rotating B buffers of 2 n-tiles: each is refilled with the next k-step's tiles right after its mma group, i.e. three
+        // groups (18 mma) plus the next fragment split ahead of its use
         const uint4* w = W1 + lane;
-        uint4 ba[4], bb[4];
-        load_bfrag<4>(ba, w);
+        uint4 b0[2], b1[2], b2[2], b3[2];
+        load_bfrag<2>(b0, w); load_bfrag<2>(b1, w + 2 * 32); load_bfrag<2>(b2, w + 4 * 32); load_bfrag<2>(b3, w + 6 * 32);
 #pragma unroll 1
         for (int k0 = 0; k0 < in_dim; k0 += 16, w += 8 * 32) {
-            load_bfrag<4>(bb, w + 4 * 32);
             unsigned ah[4], al[4];
             if (vec4 && k0 + 16 <= in_dim) {
                 const float4 u = *reinterpret_cast<const float4*>(p0 + k0), v = *reinterpret_cast<const float4*>(p1 + k0);
@@ -134,9 +135,11 @@ __device__ __forceinline__ void warp_net(const float* x_s, int in_dim, const uin
                 f16_split2(ka + 2 < in_dim ? q0[2] : 0.f, ka + 3 < in_dim ? q0[3] : 0.f, ah[2], al[2]);
                 f16_split2(ka + 2 < in_dim ? q1[2] : 0.f, ka + 3 < in_dim ? q1[3] : 0.f, ah[3], al[3]);
             }
-            mma_group<4>(c, cx, ah, al, ba);
-            if (k0 + 16 < in_dim) load_bfrag<4>(ba, w + 8 * 32);
-            mma_group<4>(c + 4, cx + 4, ah, al, bb);
+            const bool more = k0 + 16 < in_dim;
+            mma_group<2>(c, cx, ah, al, b0);         if (more) load_bfrag<2>(b0, w + 8 * 32);
+            mma_group<2>(c + 2, cx + 2, ah, al, b1); if (more) load_bfrag<2>(b1, w + 10 * 32);
+            mma_group<2>(c + 4, cx + 4, ah, al, b2); if (more) load_bfrag<2>(b2, w + 12 * 32);
+            mma_group<2>(c + 6, cx + 6, ah, al, b3); if (more) load_bfrag<2>(b3, w + 14 * 32);
         }
         hidden_to_afrag(c, cx, hh, hl);
     }
@@ -527,6 +530,11 @@ int qs_rollout(const QsParams* p, const QsState* st, const QsRolloutIO* io, int 
            + (size_t)(n_av_max * 8 * q.nt3 + n_av_max * 8 + 64) * 4 + 16;      // compact fixed part, window, means, values, log-prob terms
         if (sm > 200 * 1024) return fail(QS_ERR_UNSUPPORTED, "qs_rollout: policy + window exceed shared memory");
         if (sm > 48 * 1024) cudaFuncSetAttribute(rollout_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        {   // shared-memory carve-out: just enough for the 7 resident CTAs, so that the weights find the rest of the 256 KB as L1
+            const size_t need = 7 * (sm + 1024);
+            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+            cudaFuncSetAttribute(rollout_kernel<0, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+        }
         rollout_kernel<0, false, true><<<blocks, threads, sm, s>>>(a);
         const cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? 0 : cuda_fail(e, "qs_rollout (policy) launch");
