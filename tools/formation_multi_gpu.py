@@ -4,8 +4,8 @@
         tools/formation_multi_gpu.py [--drones 16384] [--ticks 10]
 
 Checks that the sharded run (exchange = NCCL all-gather, and the push + flag kernels over NVLink peer memory) is
-bit-identical to the unsharded formation on rank 0, then times one exchange + downwash stage per mode (CUDA events, max
-over ranks).  Writes gpurun_out/formation_multi_gpu.json on rank 0.
+bit-identical to the unsharded formation on rank 0, then times one exchange + downwash stage and one whole control tick per mode
+(CUDA events, max over ranks).  Writes gpurun_out/formation_multi_gpu.json on rank 0.
 """
 import argparse
 import json
@@ -146,6 +146,29 @@ def run(args, rank, world, local):
         env.reset()
         sh = env.shard
         res["stage_us_" + mode] = timed(lambda: env._downwash_stage(sp))
+        # The whole control tick of this rank's slice (S substeps: dynamics + exchange + downwash each) on the STACKS geometry
+        # (1.6 m pitch, 1.5 m between layers), hover RPM, 5 ticks from reset.  Not on the config-4 lattice: with 0.15 m between
+        # drones of (initially exactly) equal height, the reference's downwash term alpha ~ 1/dz^2 (BaseAviary.py:803) is singular
+        # as soon as the heights differ by rounding, the drones are thrown apart and the boxes stop culling -- a property of the
+        # model, measured as 92 us -> 1.1 ms per stage after two substeps.
+        env_t = FormationShard(xyz, exchange=mode, **kw)
+        a_loc = torch.full((1, env_t.shard.count, 4), float(hover), dtype=torch.float32, device=dev)
+
+        def ticks(k):
+            for _ in range(k):
+                env_t.step(a_loc)
+        env_t.reset(); ticks(2); env_t.reset()
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ticks(5); e1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        res["tick_us_" + mode] = float(tt.item()) * 1e3
+        env_t.reset()
+        res["stage_stacks_us_" + mode] = timed(lambda: env_t._downwash_stage(sp))
+        del env_t
+        dist.barrier()
         if mode == "p2p":
             res["stage_p2p_timed_out"] = bool(env.exchange_timed_out())
 
