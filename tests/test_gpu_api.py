@@ -349,8 +349,8 @@ def test_fused_observation_gather_in_process(act, world):
 
 @pytest.mark.parametrize("cls,act,D,critic", [("MultiHoverAviary", "RPM", 2, True), ("HoverAviary", "ONE_D_RPM", 1, True), ("MultiHoverAviary", "RPM", 4, False)])
 def test_rollout_with_on_device_policy_matches_torch_mlp(cls, act, D, critic):
-    """the SB3-MlpPolicy-shaped actor/critic evaluated INSIDE qs_rollout (FP32 FFMA on the observation window in
-    shared memory) against the same network in PyTorch fp32 driving a twin env step by step with the same noise: sampled
+    """the SB3-MlpPolicy-shaped actor/critic evaluated INSIDE qs_rollout (tensor cores, F16 two-term operand
+    split, from the observation window in shared memory) against the same network in PyTorch fp32 driving a twin env step by step with the same noise: sampled
     (unclipped) actions, log-probabilities and values within 1e-5, observations / rewards / flags of every tick equal to 1e-5."""
     import gym_pybullet_drones_b200.envs as envs
     from gym_pybullet_drones_b200.policy import MlpPolicy

@@ -61,8 +61,8 @@ for k, v in ex.items():
         continue
     frac = v.get("hbm_frac", v.get("hbm_frac_algorithmic"))
     note = ("%.3f" % frac) if frac is not None else ""
-    if "mlp_tflops_fp32" in v:
-        note = "%.1f TFLOP/s fp32 in the MLP; %s" % (v["mlp_tflops_fp32"], v.get("note", ""))
+    if "mlp_tflops_fp32_equiv" in v:
+        note = "%.1f TFLOP/s fp32-equivalent in the MLP (x3 on the tensor pipe); %s" % (v["mlp_tflops_fp32_equiv"], v.get("note", ""))
     L.append("| %s | %.2f | %.3g | %s |" % (k, ms * 1e3, v["value"], note))
 for name, n in (("r02_bench_n2_own_run.json", 2), ("r02_bench_n8_own_run.json", 8)):
     d = load(name)
@@ -93,7 +93,12 @@ L += ["", "### round-2 profile files", "",
       "* `r02_a_step_fast_kernel_ncu.md` — ncu `--set full` of `step_fast_kernel<4,1,1,1,1>` at 65 536 drones (14.3 us serialised, 110 registers, FP64 pipe 25 %, issue 36 %, DRAM reads 26.9 MB = exactly state + action + span)",
       "* `r02_step_traffic.json` — the DRAM traffic figure behind `roofline.traffic`",
       "* `r02_step_timeline.md` — per-warp `%globaltimer` phase timeline of the fast kernel (pipelined, isolated, inter-grid gaps)",
-      "* `r02_bench_n1.json`, `r02_bench_n2_own_run.json`, `r02_bench_n8_own_run.json`, `r02_configs.json`, `r02_fused_gather_{2,8}gpu.json`", ""]
+      "* `r02_bench_n1.json`, `r02_bench_n2_own_run.json`, `r02_bench_n8_own_run.json`, `r02_configs.json`, `r02_fused_gather_{2,8}gpu.json`",
+      "* `r02_policy_rollout_ncu.md` — ncu `--set full` of `rollout_kernel<0,false,true>` (on-device actor, 65 536 drones, 16 ticks): tensor pipe, issue, stall split",
+      "* `r02_mma_rate.jsonl` — `tools/mma_rate.cu`: legacy `mma.sync` issue rate on this GPU (m16n8k8 TF32 and m16n8k16 F16/BF16: one per 8 cycles per SM sub-partition)",
+      "* `r02_formation_scaling.md` / `.json` — one formation over 1/2/4/8 GPUs at 16 384 / 65 536 / 262 144 drones (whole control ticks, bit-identity at every point)",
+      "* `r02_formation_config4_tick_kernels.csv` — kernel list of two control ticks on the config-4 lattice (the downwash singularity)",
+      "* `r02_z_launches.csv` — ncu launch list of `python bench.py --steps 2 --warmup 1` (per-launch durations, cold cache, serialised)", ""]
 old = open(os.path.join(P, "README.md")).read()
 marker = "# profiles/ — round 1 measurements (B200, sm_100a)"
 if marker in old:
