@@ -44,19 +44,6 @@ __device__ __forceinline__ float dw_pair(float prop_radius, float dw1, float dw2
     return dw1 * (rr * rr) * e;
 }
 
-__device__ __forceinline__ int f2key(float x) { const int i = __float_as_int(x); return i ^ ((i >> 31) & 0x7fffffff); }
-__device__ __forceinline__ float key2f(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
-__device__ __forceinline__ float warp_min(float x) { return key2f(__reduce_min_sync(0xffffffffu, f2key(x))); }
-__device__ __forceinline__ float warp_max(float x) { return key2f(__reduce_max_sync(0xffffffffu, f2key(x))); }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 __global__ void __launch_bounds__(kDwDrones * kDwSlices) downwash_kernel(const __grid_constant__ DwArgs a) {
     __shared__ float4 tile[kDwTile];
     __shared__ float cbox[kDwChunks][6];                  // xmin xmax ymin ymax zmin zmax per chunk
@@ -171,12 +158,14 @@ __global__ void __launch_bounds__(256, 4) downwash_boxed_kernel(const __grid_con
         }
         __syncthreads();
     }
+    const bool shared_src = a.src != nullptr;            // exchange buffers are written by peers: L2-coherent loads
     float4 me = make_float4(0.f, 0.f, BIG, 0.f);
-    if (live) me = ldg4(a.rows, base + n);
+    // with flags this kernel may have been resident while the producer of `rows` (the dynamics kernel with the fused publish) was
+    // still storing: read them past L1, after the flag wait above
+    if (live) me = a.ready ? __ldcg(reinterpret_cast<const float4*>(a.rows) + base + n) : ldg4(a.rows, base + n);
     const float rx0 = warp_min(live ? me.x : BIG), rx1 = warp_max(live ? me.x : -BIG);
     const float ry0 = warp_min(live ? me.y : BIG), ry1 = warp_max(live ? me.y : -BIG);
     const float rz0 = warp_min(live ? me.z : BIG), rz1 = warp_max(live ? me.z : -BIG);
-    const bool shared_src = a.src != nullptr;            // exchange buffers are written by peers: L2-coherent loads
     const float4* src = reinterpret_cast<const float4*>(shared_src ? a.src : a.rows + base * 4);
     const float4* boxes = reinterpret_cast<const float4*>(a.boxes) + (shared_src ? 0 : (long long)env * a.chunks * 2);
     const int n_src = shared_src ? a.n_src : a.D;
@@ -273,38 +262,11 @@ struct PubArgs {
 
 __global__ void __launch_bounds__(128) dw_publish_kernel(const __grid_constant__ PubArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the consumer synchronises on the flags
-    constexpr float BIG = 3e30f;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
     const bool ok = i < a.n;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ok) v = ldg4(a.pos, i);
-    const float x0 = warp_min(ok ? v.x : BIG), x1 = warp_max(ok ? v.x : -BIG);
-    const float y0 = warp_min(ok ? v.y : BIG), y1 = warp_max(ok ? v.y : -BIG);
-    const float z0 = warp_min(ok ? v.z : BIG), z1 = warp_max(ok ? v.z : -BIG);
-    const int first = i - lane;                                           // warp-uniform
-    if (first < a.n) {
-        const long long chunk = (a.offset + first) >> 5;
-        for (int r = 0; r < a.world; ++r) {
-            float4* d = reinterpret_cast<float4*>(a.dst[r]);
-            if (ok) d[a.offset + i] = v;
-            if (lane == 0) {
-                float4* b = d + a.n_total + 2 * chunk;
-                b[0] = make_float4(x0, y0, z0, 0.f);
-                b[1] = make_float4(x1, y1, z1, 0.f);
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();                                           // cumulative over the CTA's stores (barrier above)
-        const unsigned t = atomicAdd(a.counter, 1u);
-        if (t == gridDim.x - 1) {
-            *a.counter = 0u;
-            __threadfence_system();
-            for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.rank, a.seq);
-        }
-    }
+    publish_positions(v, ok, i, a.n, a.dst, a.flags, a.counter, a.world, a.rank, a.offset, a.n_total, a.seq);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -50,7 +50,63 @@ struct StepArgs {
     int early_store;     // experiments (QS_EARLY_STORE): 1 = history written back as soon as it has landed (A = 4)
     int dbg_slot;        // QS_TIMELINE builds: which timeline buffer this launch stamps
     int row_loads;       // experiments (QS_ROW_LOADS): 1 = A = 4 fetches only the 16(B-1) history bytes of every row (one bulk copy per lane)
+    // formation exchange fused into the dynamics kernel (qs_dyn_substeps_pub; general kernel only): pub_world > 0 = on
+    float* pub_dst[QS_MAX_PEERS];
+    unsigned* pub_flags[QS_MAX_PEERS];
+    unsigned* pub_counter;
+    int pub_world, pub_rank, pub_offset, pub_n_total;
+    unsigned pub_seq;
 };
+
+// order-preserving float <-> int keys for warp-wide min / max (redux.sync)
+__device__ __forceinline__ int f2key(float x) { const int i = __float_as_int(x); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float warp_min(float x) { return key2f(__reduce_min_sync(0xffffffffu, f2key(x))); }
+__device__ __forceinline__ float warp_max(float x) { return key2f(__reduce_max_sync(0xffffffffu, f2key(x))); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Formation exchange, producer side (used by dw_publish_kernel and by the dynamics kernel's epilogue): every thread pushes the
+// position v of drone `idx` of this rank's slice (ok = the drone exists) into every rank's gathered array, lane 0 of a warp the box
+// of its chunk of 32; then the last CTA of the grid to arrive raises this rank's flag on every rank with release semantics.
+// Must be reached by every thread of the CTA; a warp = 32 consecutive drones starting on a multiple of 32.
+__device__ __forceinline__ void publish_positions(float4 v, bool ok, long long idx, int n, float* const* dst, unsigned* const* flags,
+                                                  unsigned* counter, int world, int rank, int offset, int n_total, unsigned seq) {
+    constexpr float BIG = 3e30f;
+    const int lane = threadIdx.x & 31;
+    const float x0 = warp_min(ok ? v.x : BIG), x1 = warp_max(ok ? v.x : -BIG);
+    const float y0 = warp_min(ok ? v.y : BIG), y1 = warp_max(ok ? v.y : -BIG);
+    const float z0 = warp_min(ok ? v.z : BIG), z1 = warp_max(ok ? v.z : -BIG);
+    const long long first = idx - lane;                                   // warp-uniform
+    if (first < n) {
+        const long long chunk = (offset + first) >> 5;
+        for (int r = 0; r < world; ++r) {
+            float4* d = reinterpret_cast<float4*>(dst[r]);
+            if (ok) d[offset + idx] = v;
+            if (lane == 0) {
+                float4* b = d + n_total + 2 * chunk;
+                b[0] = make_float4(x0, y0, z0, 0.f);
+                b[1] = make_float4(x1, y1, z1, 0.f);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                                           // cumulative over the CTA's stores (barrier above)
+        const unsigned t = atomicAdd(counter, 1u);
+        if (t == gridDim.x - 1) {
+            *counter = 0u;
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) st_release_sys(flags[r] + rank, seq);
+        }
+    }
+}
 
 __device__ __forceinline__ float4 ldg4(const float* base, long long idx4) {
     return __ldg(reinterpret_cast<const float4*>(base) + idx4);

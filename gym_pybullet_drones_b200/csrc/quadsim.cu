@@ -493,6 +493,11 @@ int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const
 
 int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, float* state20_out, const float* dw_fz,
                     int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream) {
+    return qs_dyn_substeps_pub(p, st, rpm, state20_out, dw_fz, n_envs, drones_per_env, substeps, effects, flags, nullptr, stream);
+}
+
+int qs_dyn_substeps_pub(const QsParams* p, const QsState* st, const float* rpm, float* state20_out, const float* dw_fz,
+                        int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, const QsDwPublish* pub, void* stream) {
     if (!p || (!rpm && !(flags & QS_FLAG_RPM_FROM_LAST))) return fail(QS_ERR_NULL, "qs_dyn_substeps: NULL params/rpm");
     if ((flags & QS_FLAG_RPM_FROM_LAST) && (!st || !st->last_rpm)) return fail(QS_ERR_NULL, "qs_dyn_substeps: RPM_FROM_LAST needs QsState.last_rpm");
     if (int rc = check_state(st, 0)) return rc;
@@ -515,6 +520,21 @@ int qs_dyn_substeps(const QsParams* p, const QsState* st, const float* rpm, floa
     a.tpb = block_size_for(drones_per_env, a.cap);
     a.counter_inc = substeps;
     a.effects = effects; a.flags = flags & (QS_FLAG_RPY_F32 | QS_FLAG_RPM_FROM_LAST | QS_FLAG_ACTION_F64);
+    if (pub) {
+        if (!pub->gathered || !pub->flags || !pub->counter) return fail(QS_ERR_NULL, "qs_dyn_substeps_pub: NULL publish pointer");
+        if (pub->world <= 0 || pub->world > QS_MAX_PEERS || pub->rank < 0 || pub->rank >= pub->world) return fail(QS_ERR_SIZE, "qs_dyn_substeps_pub: bad world/rank");
+        if (n_envs != 1) return fail(QS_ERR_UNSUPPORTED, "qs_dyn_substeps_pub: one formation = one aviary (n_envs == 1)");
+        if (pub->offset < 0 || pub->n_total < pub->offset + a.N) return fail(QS_ERR_SIZE, "qs_dyn_substeps_pub: bad offset/n_total");
+        if (pub->offset % 32 != 0 || (a.N % 32 != 0 && pub->offset + a.N != pub->n_total) || a.tpb % 32 != 0)
+            return fail(QS_ERR_ALIGN, "qs_dyn_substeps_pub: slices must start on a multiple of 32 drones (a chunk never straddles ranks)");
+        for (int r = 0; r < pub->world; ++r) {
+            if (!pub->gathered[r] || !pub->flags[r]) return fail(QS_ERR_NULL, "qs_dyn_substeps_pub: NULL peer pointer");
+            if (!aligned16(pub->gathered[r])) return fail(QS_ERR_ALIGN, "qs_dyn_substeps_pub: gathered arrays must be 16-byte aligned");
+            a.pub_dst[r] = pub->gathered[r]; a.pub_flags[r] = pub->flags[r];
+        }
+        a.pub_counter = pub->counter; a.pub_world = pub->world; a.pub_rank = pub->rank; a.pub_offset = pub->offset;
+        a.pub_n_total = pub->n_total; a.pub_seq = pub->seq;
+    }
     const cudaError_t e = launch_step_general(a, true, false, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_dyn_substeps launch");
 }

@@ -300,6 +300,12 @@ __global__ void __launch_bounds__(kMaxTPB, 4) step_kernel(const __grid_constant_
     }
     // all the FP64 work of this CTA is done: let the next grid in the stream start moving in behind the stores
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (a.pub_world > 0) {
+        // sharded formation (qs_dyn_substeps_pub): the new positions go straight into every rank's gathered array, with the boxes of
+        // their chunks and this rank's flag -- the exchange for the NEXT substep's downwash costs no launch of its own
+        publish_positions(make_float4((float)d.px, (float)d.py, (float)d.pz, 0.f), live, i, (int)N, a.pub_dst, a.pub_flags, a.pub_counter,
+                          a.pub_world, a.pub_rank, a.pub_offset, a.pub_n_total, a.pub_seq);
+    }
     if (a.io.obs == nullptr || !want_epilogue) return;
     const int od = a.obs_dim;
     if (want_rows && a.stage_rows) {

@@ -534,8 +534,7 @@ class BaseAviary(Env):
                 if raw:
                     last = s == S - 1
                     fl = self._flags | (N.FLAG_RPM_FROM_LAST if s > 0 else f64_flag)      # substeps 1.. re-read the clipped rpm of substep 0
-                    rc = L.qs_dyn_substeps(C.byref(self._P), C.byref(self._st), io.action if s == 0 else None, io.obs if last else None,
-                                           self._dw_fz.data_ptr(), self._E, self._D, 1, self._effects, fl, stream)
+                    rc = self._dyn_substep(io.action if s == 0 else None, io.obs if last else None, fl, stream)
                 else:
                     fl = self._flags | (N.FLAG_RPM_FROM_LAST if s > 0 else 0) | (N.FLAG_SKIP_EPILOGUE if s < S - 1 else 0)
                     io.tick_substeps = S
@@ -546,6 +545,12 @@ class BaseAviary(Env):
         if self._log is not None:
             self._log_append()
         return self._obs_buf[self._cur]
+
+    def _dyn_substep(self, rpm_ptr, state20_ptr, flags, stream):
+        """One DYN substep with the downwash force of `_downwash_stage` (raw-RPM envs, split loop); FormationShard fuses its
+        position exchange into this launch."""
+        return self._lib.qs_dyn_substeps(C.byref(self._P), C.byref(self._st), rpm_ptr, state20_ptr, self._dw_fz.data_ptr(),
+                                         self._E, self._D, 1, self._effects, flags, stream)
 
     def _log_append(self):
         """One entry per logged drone into the attached device ring (utils.Logger.attach, qs_log_append)."""

@@ -26,6 +26,8 @@ multiple of 32 x world; the p2p stage is not CUDA-graph capturable (the sequence
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -98,6 +100,8 @@ class FormationShard(CtrlAviary):
         self._counter = torch.zeros((1,), dtype=torch.int32, device=dev)
         self._err = torch.zeros((1,), dtype=torch.int32, device=dev)
         self._seq = 0
+        self._pub_seq = -1            # sequence number under which the CURRENT positions are already in every rank's buffer (fused publish)
+        self._fuse_publish = exchange == "p2p" and os.environ.get("QS_FUSED_PUBLISH", "1") != "0"
         self._peer_keepalive = None
         self._gathered_ptrs = None
         self._flag_ptrs = None
@@ -148,6 +152,10 @@ class FormationShard(CtrlAviary):
         self._peer_keepalive = keepalive
         self._gathered_ptrs = [(C.c_void_p * w)(*[b + 4 * k * nf for b in bases]) for k in range(2)]
         self._flag_ptrs = (C.c_void_p * w)(*[b + 4 * 2 * nf for b in bases])
+        pub = N.QsDwPublish()
+        pub.flags, pub.counter = self._flag_ptrs, self._counter.data_ptr()
+        pub.n_total, pub.world, pub.rank, pub.offset = self.N_TOTAL, w, self.shard.rank, self.shard.start
+        self._pub = pub
 
     # ---- the exchange step ------------------------------------------------------------------------------------------
     def _downwash_stage(self, stream):
@@ -160,8 +168,9 @@ class FormationShard(CtrlAviary):
         if self.exchange == "p2p":
             if self._gathered_ptrs is None:
                 raise RuntimeError("FormationShard(exchange='p2p'): peers are not connected (connect() / process group)")
-            N.check(L.qs_dw_publish(rows.data_ptr(), sh.count, sh.start, self._gathered_ptrs[self._seq & 1], self.N_TOTAL, self._flag_ptrs,
-                                    sh.world, sh.rank, self._seq, self._counter.data_ptr(), stream), "qs_dw_publish")
+            if self._pub_seq != self._seq:      # not already pushed by the previous dynamics launch (first stage after a reset, ...)
+                N.check(L.qs_dw_publish(rows.data_ptr(), sh.count, sh.start, self._gathered_ptrs[self._seq & 1], self.N_TOTAL, self._flag_ptrs,
+                                        sh.world, sh.rank, self._seq, self._counter.data_ptr(), stream), "qs_dw_publish")
             N.check(L.qs_downwash_rows(C.byref(self._P), rows.data_ptr(), sh.count, buf.data_ptr(), self.N_TOTAL,
                                        self._flags_dev.data_ptr(), self._seq, sh.world, self._err.data_ptr(),
                                        self._dw_fz.data_ptr(), stream), "qs_downwash_rows")
@@ -170,6 +179,27 @@ class FormationShard(CtrlAviary):
         N.check(L.qs_dw_boxes(buf.data_ptr(), self.N_TOTAL, stream), "qs_dw_boxes")
         N.check(L.qs_downwash_rows(C.byref(self._P), rows.data_ptr(), sh.count, buf.data_ptr(), self.N_TOTAL, None, 0, 0, None,
                                    self._dw_fz.data_ptr(), stream), "qs_downwash_rows")
+
+    def _dyn_substep(self, rpm_ptr, state20_ptr, flags, stream):
+        """The dynamics launch also pushes the new positions (and chunk boxes, and this rank's flag) to every rank, under the
+        sequence number of the NEXT downwash stage: the exchange costs no launch of its own (qs_dyn_substeps_pub)."""
+        if not self._fuse_publish or self._gathered_ptrs is None:
+            return super()._dyn_substep(rpm_ptr, state20_ptr, flags, stream)
+        sh, nxt = self.shard, self._seq + 1
+        pub = self._pub
+        pub.gathered, pub.seq = self._gathered_ptrs[nxt & 1], nxt
+        rc = self._lib.qs_dyn_substeps_pub(C.byref(self._P), C.byref(self._st), rpm_ptr, state20_ptr, self._dw_fz.data_ptr(),
+                                           self._E, self._D, 1, self._effects, flags, C.byref(pub), stream)
+        self._pub_seq = nxt
+        return rc
+
+    def reset(self, *args, **kwargs):
+        self._pub_seq = -1            # the reset positions have not been pushed
+        return super().reset(*args, **kwargs)
+
+    def reorder_by_morton(self, *args, **kwargs):
+        self._pub_seq = -1
+        return super().reorder_by_morton(*args, **kwargs)
 
     def _all_gather_positions(self, rows, out):
         all_gather_envs(rows, self.shard, group=self.group, out=out)

@@ -349,6 +349,21 @@ int qs_downwash_rows(const QsParams* p, const float* rows_pos, int n_rows, const
 int qs_dw_publish(const float* pos, int n, int offset, float* const* gathered, int n_total, unsigned* const* flags, int world, int rank,
                   unsigned seq, unsigned* counter, void* stream);
 
+/* The same push fused into the dynamics kernel: qs_dyn_substeps (one formation = one aviary, n_envs == 1, this rank's slice of
+ * drones_per_env drones) whose epilogue publishes the NEW positions -- exactly what qs_dw_publish would push from QsState.pos_f32
+ * after the call -- under sequence number pub->seq.  The exchange for the next substep's qs_downwash_rows then costs no launch
+ * of its own.  pub == NULL: plain qs_dyn_substeps. */
+typedef struct QsDwPublish {
+    float* const* gathered;     /* [world] device pointers (HOST array), as for qs_dw_publish */
+    unsigned* const* flags;     /* [world] */
+    unsigned* counter;          /* one zeroed device word (arrival count; may be shared with qs_dw_publish calls of the same stream) */
+    int n_total, world, rank, offset;
+    unsigned seq;
+    int pad_;
+} QsDwPublish;
+int qs_dyn_substeps_pub(const QsParams* p, const QsState* st, const float* rpm, float* state20_out, const float* dw_fz,
+                        int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, const QsDwPublish* pub, void* stream);
+
 /* CUDA IPC for the exchange buffers of one-process-per-GPU runs: export the 64-byte handle of the allocation that
  * contains ptr plus ptr's byte offset in it; import maps a peer's handle into this process (peer access enabled
  * lazily) and returns the peer's ptr.  Import a given handle once per process. */

@@ -127,11 +127,13 @@ def _run_local(FormationShard, Physics, xyz, acts, **kw):
     return obs.clone(), (env.pos.clone(), env.quat.clone(), env.vel.clone(), env.rpy_rates.clone())
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
-def test_formation_shards_p2p_protocol_one_gpu(world):
+@pytest.mark.parametrize("world,fused", [(1, True), (2, True), (3, True), (2, False)])
+def test_formation_shards_p2p_protocol_one_gpu(world, fused):
     """The push + flag exchange with `world` in-process shards on ONE device, each on its own stream: the states after
     6 ticks x 5 substeps are bit-identical to the unsharded formation (chunks and row groups are 32 consecutive drones of
-    the GLOBAL index, so the summation order does not depend on the partition), no wait timed out."""
+    the GLOBAL index, so the summation order does not depend on the partition), no wait timed out.  fused: the positions are
+    pushed by the dynamics kernel's epilogue (qs_dyn_substeps_pub; one explicit qs_dw_publish after the reset only), else by a
+    qs_dw_publish launch per substep."""
     N, _, FormationShard, _, Physics, O = _imports()
     xyz = stacks(16, 12)                                  # 768 drones: 768 / 384 / 256 per rank, all multiples of 32
     n, T = len(xyz), 6
@@ -144,6 +146,9 @@ def test_formation_shards_p2p_protocol_one_gpu(world):
     if world > 1:
         for s in shards:
             s.connect(shards)
+    for s in shards:
+        assert s._fuse_publish
+        s._fuse_publish = fused
     streams = [torch.cuda.Stream() for _ in shards]
     torch.cuda.synchronize()
     for s in shards:
