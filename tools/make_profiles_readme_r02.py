@@ -98,7 +98,22 @@ L += ["", "### round-2 profile files", "",
       "* `r02_mma_rate.jsonl` — `tools/mma_rate.cu`: legacy `mma.sync` issue rate on this GPU (m16n8k8 TF32 and m16n8k16 F16/BF16: one per 8 cycles per SM sub-partition)",
       "* `r02_formation_scaling.md` / `.json` — one formation over 1/2/4/8 GPUs at 16 384 / 65 536 / 262 144 drones (whole control ticks, bit-identity at every point)",
       "* `r02_formation_config4_tick_kernels.csv` — kernel list of two control ticks on the config-4 lattice (the downwash singularity)",
-      "* `r02_z_launches.csv` — ncu launch list of `python bench.py --steps 2 --warmup 1` (per-launch durations, cold cache, serialised)", ""]
+      "* `r02_z_launches.csv` — ncu launch list (`--metrics gpu__time_duration.sum --clock-control none -c 1500`) of `python bench.py --steps 40 --warmup 3 --no-extras --no-cpu-baseline` at the final commit (per-launch durations are cold-cache and serialised: shares, not absolutes; the first 1500 launches = set-up of the 8 batches and their 128 action tensors + the first timed windows):", ""]
+lp = os.path.join(P, "r02_z_launches.csv")
+if os.path.isfile(lp):
+    import collections
+    import csv
+    import re
+    acc = collections.defaultdict(lambda: [0, 0.0])
+    for r in csv.DictReader(l for l in open(lp) if l.startswith('"')):
+        n = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("<unnamed>::", "").replace("qsi::", "")
+        acc[n][0] += 1
+        acc[n][1] += float(r["Metric Value"])
+    tot = sum(v[1] for v in acc.values())
+    L += ["  | kernel | launches | share of GPU time | mean duration under ncu |", "  |---|---|---|---|"]
+    for n, (c, ns) in sorted(acc.items(), key=lambda kv: -kv[1][1])[:8]:
+        L.append("  | `%s` | %d | %.1f %% | %.2f us |" % (n[:80], c, 100 * ns / tot, ns / c / 1e3))
+    L.append("")
 old = open(os.path.join(P, "README.md")).read()
 marker = "# profiles/ — round 1 measurements (B200, sm_100a)"
 if marker in old:
