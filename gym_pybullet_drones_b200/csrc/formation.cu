@@ -286,6 +286,9 @@ struct AdjArgs {
 };
 
 constexpr int kAdjCols = 512, kAdjRows = 256;
+#ifndef QS_ADJ_DEFAULT
+#define QS_ADJ_DEFAULT 1
+#endif
 
 __global__ void __launch_bounds__(256) adjacency_kernel(const __grid_constant__ AdjArgs a) {
     __shared__ float4 rows_s[kAdjRows];
@@ -338,6 +341,129 @@ __global__ void __launch_bounds__(256) adjacency_kernel(const __grid_constant__ 
                     const bool near = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez))) < a.radius;
                     const unsigned bit = near ? (1u << (8 * (q & 3))) : 0u;
                     if ((q >> 2) == 0) w[0] |= bit; else if ((q >> 2) == 1) w[1] |= bit; else if ((q >> 2) == 2) w[2] |= bit; else w[3] |= bit;
+                }
+            }
+        }
+        const int dj = i - j0;                                              // identity (BaseAviary.py:666)
+        if ((unsigned)dj < 16u) {
+            const unsigned bit = 1u << (8 * (dj & 3));
+            if ((dj >> 2) == 0) w[0] |= bit; else if ((dj >> 2) == 1) w[1] |= bit; else if ((dj >> 2) == 2) w[2] |= bit; else w[3] |= bit;
+        }
+        unsigned char* dst = a.out + ((size_t)(base + i)) * a.D + j0;
+        if (vec) {
+            if (j0 < a.D) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (int q = 0; q < 16 && j0 + q < a.D; ++q) dst[q] = (unsigned char)((w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+        }
+    }
+}
+
+
+// ---- adjacency, second version: packed float32 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2, PTX *.f32x2) -----------------------
+// Same tiles, same decision rule, about half the instructions per pair.  A lane's 16 columns are 8 register PAIRS per
+// coordinate; one packed instruction handles two pairs: 3 x FADD2 (differences: the row is stored NEGATED and duplicated in
+// shared memory, so it arrives as packed operands by LDS.128 + LDS.64), FMUL2 + 2 x FFMA2 (squared distance),
+// FADD2 s = d2 - r2lo and FADD2 u = s - (r2hi - r2lo).  The SIGN BITS carry the decisions: sign(s) = "near",
+// ~sign(s) & sign(u) = "inside the float32 band" (accumulated over the 16 pairs with one LOP3 per pair, tested once per row);
+// the 16 result bytes are built from the sign bits by PRMT with sign replication (3 PRMT + 1 LOP3 per 4 pairs) -- no FSETP,
+// no SEL.  Rows whose band bit came up are re-evaluated exactly like in the first version (float32 band per pair, then the
+// reference's float64 arithmetic on the float64 positions).  The tile's 512 column positions are converted to float32 once
+// per CTA through shared memory (the first version converted them in every warp: 48 F2F.F32.F64 per thread).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, unsigned& lo, unsigned& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned c) { unsigned r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+__global__ void __launch_bounds__(256) adjacency2_kernel(const __grid_constant__ AdjArgs a) {
+    __shared__ __align__(16) float4 rows_a[kAdjRows];          // {-x, -x, -y, -y} of the tile's rows
+    __shared__ __align__(16) float2 rows_b[kAdjRows];          // {-z, -z}
+    __shared__ __align__(16) float cols_s[3][kAdjCols];        // x[], y[], z[] of the tile's columns (float32)
+    int b = blockIdx.x;
+    const int ct = b % a.col_tiles; b /= a.col_tiles;
+    const int rt = b % a.row_tiles;
+    const int env = b / a.row_tiles;
+    const long long base = (long long)env * a.D;
+    const int c0 = ct * kAdjCols, r0 = rt * kAdjRows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < kAdjRows; k += blockDim.x) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (r0 + k < a.D) { const D4 p = ld256(a.planes, base + r0 + k); x = (float)p.x; y = (float)p.y; z = (float)p.z; }
+        rows_a[k] = make_float4(-x, -x, -y, -y);
+        rows_b[k] = make_float2(-z, -z);
+    }
+    for (int k = threadIdx.x; k < kAdjCols; k += blockDim.x) {
+        float x = 3e30f, y = 3e30f, z = 3e30f;                  // columns past the aviary: infinitely far
+        if (c0 + k < a.D) { const D4 p = ld256(a.planes, base + c0 + k); x = (float)p.x; y = (float)p.y; z = (float)p.z; }
+        cols_s[0][k] = x; cols_s[1][k] = y; cols_s[2][k] = z;
+    }
+    __syncthreads();
+    const int j0 = c0 + 16 * lane;                             // my 16 columns = 8 packed pairs per coordinate
+    u64 cx[8], cy[8], cz[8];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const float4 fx = reinterpret_cast<const float4*>(cols_s[0])[4 * lane + v];
+        const float4 fy = reinterpret_cast<const float4*>(cols_s[1])[4 * lane + v];
+        const float4 fz = reinterpret_cast<const float4*>(cols_s[2])[4 * lane + v];
+        cx[2 * v] = pack2(fx.x, fx.y); cx[2 * v + 1] = pack2(fx.z, fx.w);
+        cy[2 * v] = pack2(fy.x, fy.y); cy[2 * v + 1] = pack2(fy.z, fy.w);
+        cz[2 * v] = pack2(fz.x, fz.y); cz[2 * v + 1] = pack2(fz.z, fz.w);
+    }
+    const float r2f = (float)(a.radius * a.radius);
+    float r2lo = r2f * (1.f - 2e-4f), r2hi = r2f * (1.f + 2e-4f);           // outside [lo, hi] float32 decides
+    if (a.radius < 0.0) r2lo = r2hi = -1.f;                                 // |d| < negative radius: never
+    const u64 nlo2 = pack2(-r2lo, -r2lo);
+    const float nbw = -(r2hi - r2lo);
+    const u64 nbw2 = pack2(nbw, nbw);
+    const bool vec = (a.D % 16) == 0;
+    for (int rr = warp; rr < kAdjRows; rr += 8) {
+        const int i = r0 + rr;
+        if (i >= a.D) break;
+        const float4 ma = rows_a[rr];                                       // warp-uniform (broadcast)
+        const float2 mb = rows_b[rr];
+        const u64 mx = pack2(ma.x, ma.y), my = pack2(ma.z, ma.w), mz = pack2(mb.x, mb.y);
+        unsigned w[4];
+        unsigned band = 0u;                                                 // sign bit: some pair of mine is inside the float32 band
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                                       // 4 pairs of columns -> one word of 4 result bytes
+            unsigned sg[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = 2 * g + h;
+                const u64 dx = add2(cx[q], mx), dy = add2(cy[q], my), dz = add2(cz[q], mz);
+                const u64 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                const u64 s = add2(d2, nlo2);                               // < 0: nearer than the lower band edge
+                const u64 u = add2(s, nbw2);                                // < 0: nearer than the upper band edge
+                unsigned s0, s1, u0, u1;
+                unpack2(s, s0, s1); unpack2(u, u0, u1);
+                band |= ~s0 & u0;
+                band |= ~s1 & u1;
+                sg[2 * h] = s0; sg[2 * h + 1] = s1;
+            }
+            // byte k of the word = sign of sg[k] replicated (PRMT selector nibble: 8 = replicate the sign of the chosen byte)
+            const unsigned t01 = prmt(sg[0], sg[1], 0x00FBu);               // byte0 <- sign(sg0.byte3), byte1 <- sign(sg1.byte3)
+            const unsigned t23 = prmt(sg[2], sg[3], 0x00FBu);
+            w[g] = prmt(t01, t23, 0x5410u) & 0x01010101u;
+        }
+        if (__any_sync(0xffffffffu, (int)band < 0)) {                       // rare: the reference's float64 arithmetic decides
+            if ((int)band < 0) {
+                const float mxs = -ma.x, mys = -ma.z, mzs = -mb.x;
+                const D4 md = ld256(a.planes, base + i);
+#pragma unroll 1
+                for (int q = 0; q < 16; ++q) {
+                    if (j0 + q >= a.D) break;
+                    const float dx = cols_s[0][16 * lane + q] - mxs, dy = cols_s[1][16 * lane + q] - mys, dz = cols_s[2][16 * lane + q] - mzs;
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (d2 < r2lo || d2 > r2hi) continue;                   // float32 decided this one
+                    const D4 od = ld256(a.planes, base + j0 + q);           // BaseAviary.py:670
+                    const double ex = md.x - od.x, ey = md.y - od.y, ez = md.z - od.z;
+                    const bool near = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez))) < a.radius;
+                    const unsigned bit = 1u << (8 * (q & 3));
+                    const unsigned keep = ~bit, set = near ? bit : 0u;
+                    if ((q >> 2) == 0) w[0] = (w[0] & keep) | set; else if ((q >> 2) == 1) w[1] = (w[1] & keep) | set;
+                    else if ((q >> 2) == 2) w[2] = (w[2] & keep) | set; else w[3] = (w[3] & keep) | set;
                 }
             }
         }
@@ -500,7 +626,10 @@ int qs_adjacency(const QsState* st, int n_envs, int drones_per_env, double radiu
     a.col_tiles = (drones_per_env + kAdjCols - 1) / kAdjCols; a.row_tiles = (drones_per_env + kAdjRows - 1) / kAdjRows;
     const long long blocks = (long long)n_envs * a.col_tiles * a.row_tiles;
     if (blocks > 0x7fffffffLL) return fail(QS_ERR_SIZE, "qs_adjacency: too many tiles");
-    adjacency_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    // QS_ADJ_V=1: the first version (scalar float32 arithmetic, FSETP + SEL packing), kept for A/B measurements
+    static const int version = getenv("QS_ADJ_V") ? atoi(getenv("QS_ADJ_V")) : QS_ADJ_DEFAULT;
+    if (version == 1) adjacency_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    else adjacency2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_adjacency launch");
 }

@@ -133,3 +133,36 @@ def test_round2_entry_points_validate_arguments_without_a_gpu():
     rio.T, rio.act_buffer_size = 4, 15
     rio.policy = C.addressof(pol)
     assert lib.qs_rollout(C.byref(P), C.byref(st), C.byref(rio), 0, 1, 4, 2, 8, 0, 0, None) == -1 and b"policy" in lib.qs_last_error()
+
+
+def test_fused_publish_entry_point_validates_arguments_without_a_gpu():
+    """qs_dyn_substeps_pub (formation exchange fused into the dynamics launch): argument errors come back as negative codes with
+    a message, nothing is launched; pub == NULL is plain qs_dyn_substeps."""
+    lib = N.lib()
+    P, st = N.QsParams(), N.QsState()
+    buf = (C.c_char * 8192)()
+    base = (C.addressof(buf) + 63) & ~63
+    st.planes, st.step_counter = base, base + 4096
+    rpm = base + 1024
+    pub = N.QsDwPublish()
+    call = lambda n_envs, D, pb: lib.qs_dyn_substeps_pub(C.byref(P), C.byref(st), rpm, None, None, n_envs, D, 1, 0, 0, pb, None)
+    assert call(1, 64, C.byref(pub)) == -1 and b"publish pointer" in lib.qs_last_error()             # NULL gathered / flags / counter
+    g = (C.c_void_p * 2)(base + 2048, base + 2048)
+    f = (C.c_void_p * 2)(base + 3072, base + 3072)
+    pub.gathered, pub.flags, pub.counter = g, f, base + 3584
+    pub.n_total, pub.world, pub.rank, pub.offset, pub.seq = 128, 17, 0, 0, 1
+    assert call(1, 64, C.byref(pub)) == -3                                                           # world > QS_MAX_PEERS
+    pub.world, pub.rank = 2, 2
+    assert call(1, 64, C.byref(pub)) == -3                                                           # rank outside world
+    pub.rank = 0
+    assert call(2, 32, C.byref(pub)) == -5 and b"one aviary" in lib.qs_last_error()                  # one formation = one aviary
+    pub.offset = 96
+    assert call(1, 64, C.byref(pub)) == -3                                                           # slice beyond n_total
+    pub.offset = 16
+    assert call(1, 64, C.byref(pub)) == -2 and b"multiple of 32" in lib.qs_last_error()              # a chunk would straddle ranks
+    pub.offset = 0
+    assert call(1, 40, C.byref(pub)) == -2                                                           # ragged slice that is not the last one
+    g[1] = None
+    assert call(1, 64, C.byref(pub)) == -1 and b"peer pointer" in lib.qs_last_error()
+    g[1] = base + 2048 + 4
+    assert call(1, 64, C.byref(pub)) == -2 and b"16-byte" in lib.qs_last_error()

@@ -82,6 +82,27 @@ def test_adjacency_vs_oracle(E, D, radius):
     assert np.array_equal(adj, adj.transpose(0, 2, 1))
 
 
+@pytest.mark.parametrize("D", [864, 1000])
+def test_adjacency_pairs_on_the_threshold(D):
+    """A lattice with 0.25 m pitch and radius 1.0: thousands of pairs sit EXACTLY on the threshold (4 steps along an axis,
+    3-4-5 triangles ... -- the reference's `<` says no) and, after perturbing random coordinates by 1e-9 ... 1e-6, within a
+    few float32 ulps of it on either side.  The float32 fast decision must hand every such pair to the float64 arithmetic of
+    the reference (the band logic of both kernel versions): bit-exact against the float64 restatement."""
+    N, CtrlAviary, _, _, Physics, O = _imports()
+    k = np.arange(D)
+    pos = np.stack([0.25 * (k % 12), 0.25 * ((k // 12) % 12), 0.25 * (k // 144)], axis=1).astype(np.float64)
+    rng = np.random.default_rng(11)
+    eps = rng.choice([0.0, 1e-9, -1e-9, 3e-8, -3e-8, 1e-6, -1e-6], size=pos.shape, p=[0.4, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1])
+    pos = pos + eps
+    env = CtrlAviary(num_drones=D, neighbourhood_radius=1.0, initial_xyzs=pos, physics=Physics.DYN, num_envs=1)
+    env.reset()
+    adj = env.adjacency().cpu().numpy()
+    ref = O.adjacency_matrix(pos[None], 1.0).astype(np.uint8)
+    d = np.sqrt(np.sum((pos[:, None, :] - pos[None, :, :]) ** 2, axis=-1))
+    assert np.count_nonzero(np.abs(d - 1.0) < 1e-5) > 2000              # the case really is full of threshold pairs
+    assert np.array_equal(adj, ref)
+
+
 @pytest.mark.parametrize("order", ["rows", "morton", "shuffled"])
 def test_downwash_culling_is_exact(order):
     """Chunk culling only skips pairs that fail the reference's predicate or whose Gaussian is exactly 0.0f: the culled

@@ -50,6 +50,8 @@ def main():
     ap.add_argument("--drones", type=int, default=16384)
     ap.add_argument("--ticks", type=int, default=10)
     ap.add_argument("--timing-only", action="store_true")
+    ap.add_argument("--modes", default="nccl,p2p", help="exchange modes to check and time")
+    ap.add_argument("--tag", default="", help="suffix of the output file (e.g. 'unfused' for a QS_FUSED_PUBLISH=0 run)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     os.makedirs("gpurun_out", exist_ok=True)
@@ -88,9 +90,11 @@ def run(args, rank, world, local):
             ref = env.step(a)[0]
         ref = ref.clone()
         del env
-    out_path = "gpurun_out/formation_multi_gpu_%d_%d.json" % (world, args.drones)
+    out_path = "gpurun_out/formation_multi_gpu_%d_%d%s.json" % (world, args.drones, ("_" + args.tag) if args.tag else "")
+    res["fused_publish"] = os.environ.get("QS_FUSED_PUBLISH", "1") != "0"
     log("reference done")
-    for name, mode in (() if args.timing_only else (("nccl", "nccl"), ("p2p", "p2p"))):
+    modes = [m for m in args.modes.split(",") if m in ("nccl", "p2p")]
+    for name, mode in (() if args.timing_only else tuple((m, m) for m in modes)):
         log("mode", name, "construct")
         env = FormationShard(xyz, exchange=mode, **kw)
         log("mode", name, "connected")
@@ -140,7 +144,7 @@ def run(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) * 1e3
 
-    for mode in ["local"] * (world == 1) + ["nccl", "p2p"]:
+    for mode in ["local"] * (world == 1) + modes:
         log("timing", mode)
         env = FormationShard(xyz4, exchange=mode, **kw)
         env.reset()
