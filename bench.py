@@ -381,8 +381,33 @@ def main():
            "ms_per_step": 1e3 * e2e_s / e2e_steps, "d2h_gbs": d2h / (e2e_s / e2e_steps) / 1e9, "pcie_d2h_gbs_measured": pcie_gbs,
            "pcie_frac": d2h / (e2e_s / e2e_steps) / 1e9 / pcie_gbs, "terminal_obs_aviaries_per_step": n_fin, "numa_binding": numa,
            "api": "MultiHoverAviary.step(page-locked ndarray) -> ndarrays (qs_step_host: H2D actions, tick, device-side compaction of the "
-                  "finished aviaries, D2H obs/reward/flags + their terminal observations; host_copy=False)"}
+                  "finished aviaries, D2H obs/reward/flags + their terminal observations; the batch is cut into chunks of whole warps whose "
+                  "observation copies run under the next chunk's H2D + tick; host_copy=False)"}
     del hbuf
+    # the same loop with the chunk count of qs_step_host's H2D -> tick -> D2H pipeline forced (QS_HOST_CHUNKS is read per call;
+    # 1 = one copy up, one launch, one copy down); the headline above is the library default
+    try:
+        sweep = {}
+        old_env = os.environ.get("QS_HOST_CHUNKS")
+        n_sw = max(10, min(a.steps, 100))
+        for c in (1, 2, 4, 8):
+            os.environ["QS_HOST_CHUNKS"] = str(c)
+            for k in range(4):
+                envs[k % R].step(h_acts[k % R][k % K_ACT])
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(n_sw):
+                envs[k % R].step(h_acts[k % R][(k // R) % K_ACT])
+            barrier()
+            sw = all_max(time.perf_counter() - t0)
+            sweep[str(c)] = {"ms_per_step": 1e3 * sw / n_sw, "value": DRONES_PER_GPU * world * n_sw / sw}
+        if old_env is None:
+            del os.environ["QS_HOST_CHUNKS"]
+        else:
+            os.environ["QS_HOST_CHUNKS"] = old_env
+        e2e["host_chunks_sweep"] = sweep
+    except Exception as ex:  # noqa: BLE001
+        e2e["host_chunks_sweep"] = {"error": repr(ex)}
     # the same loop with host_obs="head": only the 12-float kinematic head of every observation crosses PCIe (the rest of a KIN
     # observation is the action history the caller supplied itself) -- reported next to the headline e2e, never instead of it
     try:

@@ -287,7 +287,7 @@ struct AdjArgs {
 
 constexpr int kAdjCols = 512, kAdjRows = 256;
 #ifndef QS_ADJ_DEFAULT
-#define QS_ADJ_DEFAULT 1
+#define QS_ADJ_DEFAULT 2
 #endif
 
 __global__ void __launch_bounds__(256) adjacency_kernel(const __grid_constant__ AdjArgs a) {
@@ -377,7 +377,8 @@ __device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %
 __device__ __forceinline__ void unpack2(u64 v, unsigned& lo, unsigned& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
 __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned c) { unsigned r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 
-__global__ void __launch_bounds__(256) adjacency2_kernel(const __grid_constant__ AdjArgs a) {
+template <bool MIX, int MINB>
+__global__ void __launch_bounds__(256, MINB) adjacency2_kernel(const __grid_constant__ AdjArgs a) {
     __shared__ __align__(16) float4 rows_a[kAdjRows];          // {-x, -x, -y, -y} of the tile's rows
     __shared__ __align__(16) float2 rows_b[kAdjRows];          // {-z, -z}
     __shared__ __align__(16) float cols_s[3][kAdjCols];        // x[], y[], z[] of the tile's columns (float32)
@@ -432,6 +433,25 @@ __global__ void __launch_bounds__(256) adjacency2_kernel(const __grid_constant__
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int q = 2 * g + h;
+                if (MIX && h == 1) {
+                    // every second column pair with SCALAR instructions: the packed ones issue to the FMA-heavy pipe only (ncu:
+                    // fmaheavy 54 % busy, math-pipe throttle the top stall, fmalite idle), scalar FADD / FMUL / FFMA can take the
+                    // lite pipe -- same arithmetic, same bits
+                    unsigned cxl, cxh, cyl, cyh, czl, czh;
+                    unpack2(cx[q], cxl, cxh); unpack2(cy[q], cyl, cyh); unpack2(cz[q], czl, czh);
+                    const float nlo = -r2lo;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const float dx = __uint_as_float(k ? cxh : cxl) + ma.x, dy = __uint_as_float(k ? cyh : cyl) + ma.z,
+                                    dz = __uint_as_float(k ? czh : czl) + mb.x;
+                        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        const float sf = d2 + nlo, uf = sf + nbw;
+                        const unsigned sb = __float_as_uint(sf), ub = __float_as_uint(uf);
+                        band |= ~sb & ub;
+                        sg[2 + k] = sb;
+                    }
+                    continue;
+                }
                 const u64 dx = add2(cx[q], mx), dy = add2(cy[q], my), dz = add2(cz[q], mz);
                 const u64 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
                 const u64 s = add2(d2, nlo2);                               // < 0: nearer than the lower band edge
@@ -627,9 +647,15 @@ int qs_adjacency(const QsState* st, int n_envs, int drones_per_env, double radiu
     const long long blocks = (long long)n_envs * a.col_tiles * a.row_tiles;
     if (blocks > 0x7fffffffLL) return fail(QS_ERR_SIZE, "qs_adjacency: too many tiles");
     // QS_ADJ_V=1: the first version (scalar float32 arithmetic, FSETP + SEL packing), kept for A/B measurements
-    static const int version = getenv("QS_ADJ_V") ? atoi(getenv("QS_ADJ_V")) : QS_ADJ_DEFAULT;
-    if (version == 1) adjacency_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
-    else adjacency2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    // 2: all packed; 3: half packed, half scalar; 4 / 5: the same two with registers capped for 3 CTAs per SM (read per call: A/B tool)
+    const char* ve = getenv("QS_ADJ_V");
+    const int version = ve ? atoi(ve) : QS_ADJ_DEFAULT;
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (version == 1) adjacency_kernel<<<(unsigned)blocks, 256, 0, cs>>>(a);
+    else if (version == 3) adjacency2_kernel<true, 2><<<(unsigned)blocks, 256, 0, cs>>>(a);
+    else if (version == 4) adjacency2_kernel<false, 3><<<(unsigned)blocks, 256, 0, cs>>>(a);
+    else if (version == 5) adjacency2_kernel<true, 3><<<(unsigned)blocks, 256, 0, cs>>>(a);
+    else adjacency2_kernel<false, 2><<<(unsigned)blocks, 256, 0, cs>>>(a);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_adjacency launch");
 }

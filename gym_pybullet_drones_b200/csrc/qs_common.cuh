@@ -50,6 +50,8 @@ struct StepArgs {
     int early_store;     // experiments (QS_EARLY_STORE): 1 = history written back as soon as it has landed (A = 4)
     int dbg_slot;        // QS_TIMELINE builds: which timeline buffer this launch stamps
     int row_loads;       // experiments (QS_ROW_LOADS): 1 = A = 4 fetches only the 16(B-1) history bytes of every row (one bulk copy per lane)
+    int first_warp, n_warps;   // fast kernels: launch over warps [first_warp, first_warp + n_warps) of the batch only (n_warps = 0: all);
+                         // qs_step_host pipelines chunks of the batch against their host copies
     // formation exchange fused into the dynamics kernel (qs_dyn_substeps_pub; general kernel only): pub_world > 0 = on
     float* pub_dst[QS_MAX_PEERS];
     unsigned* pub_flags[QS_MAX_PEERS];

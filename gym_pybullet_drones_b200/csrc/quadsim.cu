@@ -314,8 +314,11 @@ int qs_sizeof_params(void) { return (int)sizeof(QsParams); }
 int qs_sizeof_state(void) { return (int)sizeof(QsState); }
 int qs_sizeof_step_io(void) { return (int)sizeof(QsStepIO); }
 
-int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_type, int task,
-            int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream) {
+// Validates the arguments of one control tick and fills the kernel argument block; nothing is launched.
+// fast = the configuration is one of step_fast.cu's (else step_general.cu takes it).
+static int prepare_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_type, int task,
+                        int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags,
+                        StepArgs& a, bool& state20_out, bool& pid_act_out, bool& fast) {
     if (!p || !io) return fail(QS_ERR_NULL, "qs_step: NULL params/io");
     const bool autoreset = flags & (QS_FLAG_AUTORESET_SAME_STEP | QS_FLAG_AUTORESET_NEXT_STEP);
     if (int rc = check_state(st, autoreset ? 1 : 0)) return rc;
@@ -345,7 +348,6 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
         return fail(QS_ERR_UNSUPPORTED, "qs_step: in-CTA downwash needs drones_per_env <= 128 (else pass dw_fz from qs_downwash, substeps = 1)");
     if ((effects & QS_EFFECT_DW) && io->dw_fz && substeps != 1) return fail(QS_ERR_UNSUPPORTED, "qs_step: external dw_fz requires substeps == 1");
     if ((flags & QS_FLAG_AUTORESET_NEXT_STEP) && !st->pending_reset) return fail(QS_ERR_NULL, "qs_step: NEXT_STEP autoreset needs pending_reset");
-    StepArgs a;
     memset(&a, 0, sizeof(a));
     a.P = *p; a.st = *st; a.io = *io;
     a.act_type = act_type; a.task = task; a.n_envs = n_envs; a.D = drones_per_env; a.substeps = substeps;
@@ -385,8 +387,17 @@ int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_ty
         if (!aligned16(io->obs_gather)) return fail(QS_ERR_ALIGN, "qs_step: obs_gather must be 16-byte aligned");
         if (io->gather_flag && !io->gather_counter) return fail(QS_ERR_NULL, "qs_step: gather_flag needs gather_counter");
     }
-    const cudaError_t e = (!fast_off && step_fast_eligible(a)) ? launch_step_fast(a, (cudaStream_t)stream)
-                                                               : launch_step_general(a, state20, pid_act, (cudaStream_t)stream);
+    fast = !fast_off && step_fast_eligible(a);
+    state20_out = state20; pid_act_out = pid_act;
+    return 0;
+}
+
+int qs_step(const QsParams* p, const QsState* st, const QsStepIO* io, int act_type, int task,
+            int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream) {
+    StepArgs a;
+    bool state20 = false, pid_act = false, fast = false;
+    if (int rc = prepare_step(p, st, io, act_type, task, n_envs, drones_per_env, substeps, effects, flags, a, state20, pid_act, fast)) return rc;
+    const cudaError_t e = fast ? launch_step_fast(a, (cudaStream_t)stream) : launch_step_general(a, state20, pid_act, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "qs_step launch");
 }
 
@@ -402,6 +413,25 @@ int qs_host_is_pinned(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
     return at.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
+constexpr int kMaxHostChunks = 8, kMaxHostDevices = 32;
+#ifndef QS_HOST_CHUNKS_DEFAULT
+#define QS_HOST_CHUNKS_DEFAULT 4
+#endif
+// events (timing disabled) that order chunk c's observation copy after chunk c's kernel: one set per host thread and device,
+// created on first use, never destroyed (a handful of driver objects for the life of the process)
+static cudaEvent_t* host_chunk_events() {
+    static thread_local cudaEvent_t ev[kMaxHostDevices][kMaxHostChunks];
+    static thread_local bool made[kMaxHostDevices] = {};
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxHostDevices) { (void)cudaGetLastError(); return nullptr; }
+    if (!made[dev]) {
+        for (int c = 0; c < kMaxHostChunks; ++c)
+            if (cudaEventCreateWithFlags(&ev[dev][c], cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        made[dev] = true;
+    }
+    return ev[dev];
 }
 
 int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const QsHostIO* h, int act_type, int task,
@@ -425,12 +455,51 @@ int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const
     static int trace_n = 0;
     auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
     const double t0 = trace ? now() : 0.0;
-    cudaError_t e = cudaMemcpyAsync(h->action_dev, h->action_host, (size_t)N * A * 4, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) return cuda_fail(e, "qs_step_host H2D action");
     QsStepIO dio = *io;
     dio.action = h->action_dev;
-    if (int rc = qs_step(p, st, &dio, act_type, task, n_envs, drones_per_env, substeps, effects, flags, stream)) return rc;
+    StepArgs sa;
+    bool sa_state20 = false, sa_pid = false, sa_fast = false;
+    if (int rc = prepare_step(p, st, &dio, act_type, task, n_envs, drones_per_env, substeps, effects, flags, sa, sa_state20, sa_pid, sa_fast)) return rc;
+    cudaError_t e = cudaSuccess;
+    // Chunked pipeline (fast kernels, full-observation transfer): the batch is cut into `chunks` ranges of whole warps; chunk c's
+    // actions go up, its tick runs, and its observation rows come down on the side stream while chunk c+1's actions go up and its
+    // tick runs -- the 19 MB device->host copy, which bounds the call, starts after 1/chunks of the H2D + kernel time instead of
+    // after all of it, and the launch / copy-issue gaps between dependent operations hide behind it.
+    // QS_HOST_CHUNKS=n forces n (1 = off); default 4 from 16 384 drones up.
+    int chunks = 1;
+    cudaEvent_t* cev = nullptr;
+    const long long warps_total = (N + 31) / 32;
+    if (sa_fast && h->side_stream && h->ev_join && !(h->obs_head_host && !state20) && !io->obs_gather) {
+        const char* ce = getenv("QS_HOST_CHUNKS");
+        chunks = ce ? atoi(ce) : (N >= 16384 ? QS_HOST_CHUNKS_DEFAULT : 1);
+        if (chunks > kMaxHostChunks) chunks = kMaxHostChunks;
+        if (chunks > warps_total) chunks = (int)warps_total;
+        if (chunks > 1 && !(cev = host_chunk_events())) chunks = 1;
+    }
     bool forked = false, small_done = false;
+    const bool chunked = chunks > 1;
+    if (chunked) {
+        cudaStream_t cs = (cudaStream_t)h->side_stream;
+        for (int c = 0; c < chunks; ++c) {
+            const long long w0 = warps_total * c / chunks, w1 = warps_total * (c + 1) / chunks;
+            const long long d0 = w0 * 32, d1 = (w1 * 32 < N) ? w1 * 32 : N;
+            e = cudaMemcpyAsync(h->action_dev + d0 * A, h->action_host + d0 * A, (size_t)(d1 - d0) * A * 4, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return cuda_fail(e, "qs_step_host H2D action");
+            sa.first_warp = (int)w0; sa.n_warps = (int)(w1 - w0);
+            e = launch_step_fast(sa, s);
+            if (e != cudaSuccess) return cuda_fail(e, "qs_step_host launch");
+            cudaEventRecord(cev[c], s);
+            cudaStreamWaitEvent(cs, cev[c], 0);
+            cudaMemcpyAsync(h->obs_host + d0 * od, io->obs + d0 * od, (size_t)(d1 - d0) * od * 4, cudaMemcpyDeviceToHost, cs);
+        }
+        cudaEventRecord((cudaEvent_t)h->ev_join, cs);
+        forked = true;                                                   // joined below, after the small outputs have been queued on s
+    } else {
+        e = cudaMemcpyAsync(h->action_dev, h->action_host, (size_t)N * A * 4, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return cuda_fail(e, "qs_step_host H2D action");
+        e = sa_fast ? launch_step_fast(sa, s) : launch_step_general(sa, sa_state20, sa_pid, s);
+        if (e != cudaSuccess) return cuda_fail(e, "qs_step_host launch");
+    }
     if (want_final) {
         // terminal observations: device-side compaction of the done flags (ascending), then the gather kernel writes the rows,
         // their indices and the count into the mapped host arrays.  On a side stream this overlaps the copies below.
@@ -441,10 +510,12 @@ int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const
             return cuda_fail(e, "qs_step_host: final_obs_host / final_env_host / n_final_host must be pinned, mapped host memory");
         cudaStream_t fs = s;
         if (h->side_stream && h->ev_fork) {
-            fs = (cudaStream_t)h->side_stream;
-            cudaEventRecord((cudaEvent_t)h->ev_fork, s);
-            cudaStreamWaitEvent(fs, (cudaEvent_t)h->ev_fork, 0);
-            forked = true;
+            if (!chunked) {
+                fs = (cudaStream_t)h->side_stream;
+                cudaEventRecord((cudaEvent_t)h->ev_fork, s);
+                cudaStreamWaitEvent(fs, (cudaEvent_t)h->ev_fork, 0);
+                forked = true;
+            }
             // the per-aviary outputs travel by kernel stores into the (mapped) host arrays on the side stream as well
             float* rew_h = nullptr; unsigned char *te_h = nullptr, *tr_h = nullptr, *dn_h = nullptr;
             static const bool small_kernel = !(getenv("QS_SMALL_OUT") && atoi(getenv("QS_SMALL_OUT")) == 0);
@@ -463,7 +534,7 @@ int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const
         const int row_floats = drones_per_env * od;
         const int blocks = n_envs < 1184 ? n_envs : 1184;                                  // 148 SMs x 8, grid-stride over the k rows
         gather_rows_kernel<<<blocks, 128, 0, fs>>>(io->final_obs, h->final_env_dev, h->n_final_dev, rows_h, idx_h, k_h, row_floats);
-        if (forked) cudaEventRecord((cudaEvent_t)h->ev_join, fs);
+        if (forked && !chunked) cudaEventRecord((cudaEvent_t)h->ev_join, fs);
     } else if (h->n_final_host) {
         *h->n_final_host = 0;
     }
@@ -478,7 +549,7 @@ int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const
         if ((e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&heads_h), h->obs_head_host, 0)) != cudaSuccess)
             return cuda_fail(e, "qs_step_host: obs_head_host must be pinned, mapped host memory");
         pack_heads_kernel<<<(unsigned)((3 * N + 255) / 256), 256, 0, s>>>(io->obs, od, N, heads_h);
-    } else {
+    } else if (!chunked) {
         cudaMemcpyAsync(h->obs_host, io->obs, (size_t)N * od * 4, cudaMemcpyDeviceToHost, s);
     }
     if (forked) cudaStreamWaitEvent(s, (cudaEvent_t)h->ev_join, 0);

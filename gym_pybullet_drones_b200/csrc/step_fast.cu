@@ -50,9 +50,10 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int od = a.obs_dim;
     const long long N = a.N;
-    const long long wg = (long long)blockIdx.x * WARPS + warp;             // global warp index
+    const long long wg = (long long)a.first_warp + (long long)blockIdx.x * WARPS + warp;      // global warp index (a launch may cover a chunk)
     const long long w0 = wg * 32;                                           // first drone of this warp
     if (w0 >= N) return;                                                    // (whole warp: no barrier is shared between warps)
+    if (WARPS > 1 && a.n_warps > 0 && wg >= (long long)a.first_warp + a.n_warps) return;     // past the chunk (a later launch owns these drones)
     const long long i = w0 + lane;
     const bool live = i < N;
     const int rows = (int)((N - w0) < 32 ? (N - w0) : 32);
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(32 * WARPS) step_fast_kernel(const __grid_cons
 
 template <int A, bool TASK, bool RESET, bool RPYF, int WARPS>
 cudaError_t launch_one(const StepArgs& a, cudaStream_t s) {
-    const long long warps = (a.N + 31) / 32;
+    const long long warps = a.n_warps > 0 ? a.n_warps : (a.N + 31) / 32;
     const int blocks = (int)((warps + WARPS - 1) / WARPS);
     const bool fin = RESET && a.io.final_obs != nullptr;
     const size_t sm = (size_t)WARPS * FastSmem<A>::total_bytes(a.obs_dim, fin);

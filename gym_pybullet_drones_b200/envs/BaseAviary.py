@@ -363,11 +363,12 @@ class BaseAviary(Env):
         self._h_final = None
         if self._final_obs is not None:
             self._h_final = [torch.zeros((E, D, self._obs_dim), dtype=torch.float32).pin_memory() for _ in range(2)]
-            # compaction + gather of the terminal observations run next to the observation copy (qs_step_host)
-            self._side_stream = torch.cuda.Stream(device=dev)
-            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
-            with self._on_device():
-                self._ev_fork.record(); self._ev_join.record()          # materialise the cudaEvent_t handles
+        # qs_step_host's second stream: the compaction + gather of the terminal observations run next to the observation copy,
+        # and the chunked pipeline brings chunk c's observation rows down while chunk c+1's actions go up and its tick runs
+        self._side_stream = torch.cuda.Stream(device=dev)
+        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        with self._on_device():
+            self._ev_fork.record(); self._ev_join.record()              # materialise the cudaEvent_t handles
         self._h_action_np = self._h_action.numpy()
         self._h_action_view = self._h_action_np.reshape(E, D, self._A) if self.VECTORIZED else self._h_action_np.reshape(D, self._A)
         self._h_action_ptr = self._h_action.data_ptr()
@@ -383,7 +384,7 @@ class BaseAviary(Env):
                 h.obs_head_host = self._h_head[k].data_ptr()
             if self._final_obs is not None:
                 h.final_obs_host = self._h_final[k].data_ptr()
-                h.side_stream, h.ev_fork, h.ev_join = self._side_stream.cuda_stream, self._ev_fork.cuda_event, self._ev_join.cuda_event
+            h.side_stream, h.ev_fork, h.ev_join = self._side_stream.cuda_stream, self._ev_fork.cuda_event, self._ev_join.cuda_event
             self._hio.append(h)
             self._h_np.append((self._h_obs[k].numpy().reshape(E, D, self._obs_dim), self._h_reward[k].numpy(),
                                self._h_term[k].numpy(), self._h_trunc[k].numpy()))

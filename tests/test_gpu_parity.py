@@ -441,6 +441,39 @@ def test_numpy_vector_api_roundtrip_equals_tensor_api():
     assert seen > 20
 
 
+@pytest.mark.parametrize("act,E,D,chunks,autoreset", [("RPM", 128, 2, "3", "same_step"), ("ONE_D_RPM", 1024, 4, "8", "same_step"),
+                                                     ("RPM", 8192, 2, None, "same_step"), ("RPM", 1000, 1, "4", None),
+                                                     ("RPM", 96, 32, "5", "same_step")])
+def test_numpy_vector_api_chunked_pipeline_equals_tensor_api(act, E, D, chunks, autoreset, monkeypatch):
+    """qs_step_host cuts the batch into chunks of whole warps and pipelines H2D(actions) -> tick -> D2H(observations) chunk by
+    chunk (default: 4 chunks from 16 384 drones up; QS_HOST_CHUNKS forces a count): what comes back is exactly what the
+    tensor API returns -- observations, rewards, flags, indices and rows of the terminal observations -- for chunk counts
+    that do not divide the number of warps, a ragged last warp (1000 drones), aviaries of 32 drones, and without autoreset."""
+    _, _, _, MultiHoverAviary, ActionType, _, Physics, _ = _imports()
+    if chunks is None:
+        monkeypatch.delenv("QS_HOST_CHUNKS", raising=False)
+    else:
+        monkeypatch.setenv("QS_HOST_CHUNKS", chunks)
+    A = 4 if act == "RPM" else 1
+    rng = np.random.default_rng(8)
+    kw = dict(num_drones=D, physics=Physics.DYN, act=getattr(ActionType, act), num_envs=E, autoreset=autoreset)
+    e1, e2 = MultiHoverAviary(**kw), MultiHoverAviary(**kw)
+    e1.reset(); e2.reset()
+    seen = 0
+    for t in range(100 if E <= 1024 else 30):
+        a = rng.uniform(-1, 1, (E, D, A)).astype(np.float32)
+        o1, r1, te1, tr1, i1 = e1.step(torch.from_numpy(a).cuda())
+        o2, r2, te2, tr2, i2 = e2.step(a)
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(te1.cpu().numpy(), te2) and np.array_equal(tr1.cpu().numpy(), tr2)
+        done = te2 | tr2
+        if autoreset and done.any():
+            seen += int(done.sum())
+            assert np.array_equal(i2["final_obs_env"], np.flatnonzero(done))
+            assert np.array_equal(i2["final_obs"], i1["final_obs"].cpu().numpy()[done])
+    assert seen > 0 or not autoreset
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # (c) size-independent properties at BASELINE.json's full sizes
 # ---------------------------------------------------------------------------------------------------------------
