@@ -287,7 +287,7 @@ struct AdjArgs {
 
 constexpr int kAdjCols = 512, kAdjRows = 256;
 #ifndef QS_ADJ_DEFAULT
-#define QS_ADJ_DEFAULT 2
+#define QS_ADJ_DEFAULT 4
 #endif
 
 __global__ void __launch_bounds__(256) adjacency_kernel(const __grid_constant__ AdjArgs a) {

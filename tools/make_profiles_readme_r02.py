@@ -77,6 +77,43 @@ for name in ("r02_fused_gather_2gpu.json", "r02_fused_gather_8gpu.json"):
               "bit-identical to NCCL `all_gather_into_tensor`: %s; a tick as the learner sees it: step only %.1f us, **fused gather %.1f us**, step + NCCL all-gather %.1f us; learner inbound %.1f MB per tick = %.0f GB/s fused vs %.0f GB/s NCCL (peer-copy peak measured on this pool: 770 GB/s)." %
               (d["fused_equals_nccl_all_gather"], d["ms_per_tick_step_only"] * 1e3, d["ms_per_tick_fused_gather"] * 1e3, d["ms_per_tick_step_plus_nccl_all_gather_obs"] * 1e3,
                d["learner_inbound_bytes_per_tick"] / 1e6, d["fused_inbound_GBps"], d["nccl_inbound_GBps"])]
+sw = e.get("host_chunks_sweep")
+if isinstance(sw, dict) and "1" in sw:
+    L += ["", "### `qs_step_host` chunk count (same run, same envs; `QS_HOST_CHUNKS` forced per call; default 4 from 16 384 drones up)", "",
+          "| chunks | ms per step | drone-steps/s |", "|---|---|---|"]
+    for c, v in sw.items():
+        L.append("| %s | %.3f | %.3g |" % (c, v["ms_per_step"], v["value"]))
+    L += ["", "One chunk = one copy up, one launch, one copy down (round-2 state before the pipeline).  `r02_e2e_trace_qs_step_host.log`: `QS_TRACE=1` lines of",
+          "`tools/e2e_quick.py` (pageable actions, no NUMA binding: 0.51 ms per step): 35 us to enqueue the whole tick, ~0.40 ms in the final stream synchronise."]
+adj = []
+try:
+    adj = [json.loads(l) for l in open(os.path.join(P, "r02_adjacency_versions.jsonl"))]
+except Exception:
+    pass
+if adj:
+    names = {1: "first version (scalar float32, FSETP + SEL packing; round-2 start)", 2: "packed float32 (FADD2 / FMUL2 / FFMA2), sign-bit decisions packed by PRMT",
+             3: "half of the column pairs packed, half scalar", 4: "version 2 with registers capped for 3 CTAs per SM (80 registers, 72 B spilled) -- **default**",
+             5: "version 3 with 3 CTAs per SM"}
+    L += ["", "### `qs_adjacency` kernel versions (`tools/adjacency_ab.py`, one process, 16 384 drones = 268 MB per query, two alternating outputs; `r02_adjacency_versions.jsonl`)", "",
+          "| `QS_ADJ_V` | kernel | us per query (config-4 lattice / uniform random) | TB/s written | of the copy peak | bit-identical to version 1 |", "|---|---|---|---|---|---|"]
+    for d in adj:
+        a, b2 = d["config4_lattice"], d["uniform_random"]
+        L.append("| %d | %s | %.1f / %.1f | %.2f | %.3f | %s |" % (d["version"], names.get(d["version"], ""), a["ms_per_query"] * 1e3, b2["ms_per_query"] * 1e3,
+                                                              a["written_gbs"] / 1e3, a["frac_of_copy_peak"], "yes" if a["equals_version_1"] and b2["equals_version_1"] else "NO"))
+    L += ["", "ncu of version 2 (`r02_adjacency2_kernel_ncu.md`): 9.9 instructions per pair (first version ~13), issue slots 54 % busy, the packed instructions go to the",
+          "FMA-heavy pipe only (54 % busy, math-pipe throttle the top stall); mixing scalar instructions in (3) or raising the occupancy (4) moves the time by < 5 %:",
+          "the kernel is bound by dependent-issue latency at 16-24 warps per SM, not by one pipe.  All five versions pass the golden / oracle / threshold tests."]
+ff, fu = load("r02_formation_1gpu_65536_fused_publish.json"), load("r02_formation_1gpu_65536_unfused_publish.json")
+if ff and fu:
+    L += ["", "### formation exchange fused into the dynamics kernel (`qs_dyn_substeps_pub`), one GPU, 65 536 drones, p2p protocol (`r02_formation_1gpu_65536_{fused,unfused}_publish.json`)", "",
+          "Control tick (5 substeps: dynamics, exchange, boxed pair kernel): **%.1f us with the positions pushed by the dynamics kernel's epilogue** vs %.1f us with a publish launch per substep" % (ff["tick_us_p2p"], fu["tick_us_p2p"]),
+          "(stand-alone publish kernel: %.1f us; unsharded single-launch path: %.1f us); bit-identical to the unsharded formation: %s.  On one GPU the publish launch mostly hid behind its" % (fu["part_us_publish_kernel"], ff["tick_us_local"], ff["p2p_bit_identical_to_unsharded"]),
+          "neighbours (programmatic dependent launch), so only ~2 us per substep come back; with peers the publish costs 14-27 us per substep (table in `r02_formation_scaling.md`,",
+          "measured before the fusion) -- the multi-GPU re-measurement did not fit into this round's GPU budget."]
+L += ["", "### GPU test log of the final tree (`r02_gpu_tests_final.log`)", "",
+      "132 tests: 131 passed; the one failure is the episode-count bookkeeping assertion of a NEW case of",
+      "`test_numpy_vector_api_chunked_pipeline_equals_tensor_api` (ONE_D_RPM: collective thrust only, no aviary finishes within 100 ticks, so `seen > 0` cannot hold) --",
+      "every per-step equality of that case held; the assertion was corrected after the run (no GPU minutes were left to re-run it)."]
 if cfg:
     L += ["", "### other BASELINE.json configs (`tools/bench_configs.py`, file `r02_configs.json`)", "",
           "| config | ms per step / call | per second | alg. bytes | HBM frac (algorithmic) | note |", "|---|---|---|---|---|---|"]
