@@ -255,7 +255,9 @@ typedef struct QsHostIO {
     float* obs_head_host;            /* optional [N][12] (pinned, mapped): when set, only the kinematic head (pos3 rpy3 vel3 ang_v3) of every
                                         observation row travels -- packed by a kernel into this array -- and obs_host is NOT written: a caller
                                         that supplied the actions already holds the action-history part of the rows (5/6 of the bytes) */
-    void* side_stream;               /* optional cudaStream_t for the compaction + gather of the terminal observations */
+    void* side_stream;               /* optional second cudaStream_t: the compaction + gather of the terminal observations run on it next to
+                                        the observation copy; with the chunked pipeline (fast-kernel configurations, >= 16 384 drones or
+                                        QS_HOST_CHUNKS=n) it carries the per-chunk observation copies instead, each behind its chunk's tick */
     void* ev_fork;                   /* optional cudaEvent_t pair (timing disabled) used to fork/join side_stream; both or neither */
     void* ev_join;
 } QsHostIO;
@@ -287,6 +289,8 @@ int qs_step_call(const QsStepCall* c, void* stream);
 
 /* qs_step with host buffers: H2D(action) -> fused tick -> D2H(reward, flags) -> D2H(obs) (+ a compact D2H of the terminal
  * observations of finished aviaries).  `io` carries the device buffers exactly as for qs_step (io->action is ignored).
+ * Large batches are pipelined in chunks of whole warps (chunk c's observation rows travel while chunk c+1's actions go up and
+ * its tick runs); the results are the same bits as one qs_step over the whole batch.
  * Unlike every other entry point this one SYNCHRONISES `stream` before returning (the host arrays are valid on return). */
 int qs_step_host(const QsParams* p, const QsState* st, const QsStepIO* io, const QsHostIO* h, int act_type, int task,
                  int n_envs, int drones_per_env, int substeps, unsigned effects, unsigned flags, void* stream);
